@@ -1,0 +1,11 @@
+"""tagan_b200 -- B200 (sm_100a) kernels behind TAGAN's per-snapshot attention-and-propagation core.
+
+Host side of the C ABI in ``include/tagan_b200.h``: drop-in ``nn.Module`` mirrors of the
+reference layers (``layers``), thin ctypes wrappers + autograd glue (``ops``) and synthetic
+workloads (``synth``).  The package name is ``tagan_b200`` because the repository's long name
+(``temporal-asymmetric-graph-attention-network_b200``) is not an importable identifier.
+"""
+from . import _lib, ops  # noqa: F401
+from .layers import GeometricAttention, TAGANGraphAttention  # noqa: F401
+
+__all__ = ["ops", "GeometricAttention", "TAGANGraphAttention"]

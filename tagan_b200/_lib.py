@@ -1,0 +1,84 @@
+"""ctypes binding of libtagan_b200.so (the C ABI declared in include/tagan_b200.h).
+
+No torch types cross this boundary: callers pass raw device pointers (``tensor.data_ptr()``),
+sizes and the raw ``cudaStream_t`` of torch's current stream.  There is deliberately no CPU
+fallback: if the library is missing or a tensor is not on a CUDA device the call raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtagan_b200.so")
+
+_p = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f32 = C.c_float
+_sz = C.c_size_t
+
+
+class TimeParams(C.Structure):
+    """struct tagan_time_params"""
+    _fields_ = [("range", _p), ("mu", _p), ("inv2sig2", _p), ("wc", _p), ("bc", _p), ("nb", _i32)]
+
+
+# name -> (restype, argtypes); must list every symbol include/tagan_b200.h declares.
+SIGNATURES = {
+    "tagan_abi_version": (_i32, []),
+    "tagan_csr_workspace_bytes": (_sz, [_i64, _i32]),
+    "tagan_csr_build": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "tagan_geo_attn_fwd": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "tagan_geo_attn_bwd": (_i32, [_p, _p, _p, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
+                                  _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "tagan_layernorm_fwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _p]),
+    "tagan_layernorm_bwd_workspace_bytes": (_sz, [_i64, _i32]),
+    "tagan_layernorm_bwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _sz,
+                                   _i64, _i32, _p]),
+    "tagan_colsum_workspace_bytes": (_sz, [_i64, _i32]),
+    "tagan_colsum": (_i32, [_p, _i64, _p, _p, _sz, _i64, _i32, _p]),
+    "tagan_gemm_workspace_bytes": (_sz, [_i32, _i64, _i64, _i64]),
+    "tagan_gemm": (_i32, [_i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _sz, _p]),
+    "tagan_axpby": (_i32, [_p, _f32, _p, _f32, _p, _i64, _p]),
+    "tagan_gelu_fwd": (_i32, [_p, _p, _i64, _p]),
+    "tagan_gelu_bwd": (_i32, [_p, _p, _p, _i64, _p]),
+    "tagan_scale_rows": (_i32, [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _p]),
+    "tagan_decay_scale": (_i32, [_p, _i64, _i32, _p, _i64, _p]),
+}
+
+_lib = None
+
+
+class TaganLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the in-tree library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TaganLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m tagan_b200.build` "
+            "(there is no CPU / PyTorch fallback for the TAGAN hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise TaganLibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+_ERRORS = {-1: "invalid argument", -2: "unsupported shape", -3: "workspace too small"}
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f"{what}: {_ERRORS.get(rc, rc)} (libtagan_b200 code {rc})")
+    raise RuntimeError(f"{what}: CUDA error {rc}")

@@ -1,0 +1,341 @@
+// (a1) Device CSR build: edge_index[2,E] (int64) -> unique(edges) U self-loops as CSR, plus the
+// transposed CSR used by the deterministic backward.  Replaces the dense N x N mask of
+// TAGANGraphAttention.forward (reference src/tagan/layers/graph_attention.py:98-102).
+//
+// Integer, HBM/atomic-bound work; every output is a pure function of the input *set* (atomics
+// only decide the order inside a bucket, and each bucket is then sorted), so results are
+// bit-exact and deterministic:
+//   count rows (atomicAdd) -> scan -> scatter into row buckets -> per-row rank sort + dedup
+//   -> scan unique counts = rowptr -> compact -> [count cols -> scan -> scatter -> per-col sort].
+#include "common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  // exclusive scan of one value per thread across a SCAN_THREADS block
+  __shared__ int warp_tot[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0;
+    int ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(FULL_MASK, ti, o);
+      if (lane >= o) ti += u;
+    }
+    if (lane < SCAN_THREADS / 32) warp_tot[lane] = ti - t;  // exclusive warp offsets
+    if (lane == 31) *total = ti;
+  }
+  __syncthreads();
+  int r = warp_tot[w] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void scan_block_sums(const int* __restrict__ in, int* __restrict__ bsum, int64_t n) {
+  __shared__ int total;
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) s += (base + i < n) ? in[base + i] : 0;
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+// out[i] = boff[block] + exclusive prefix inside the block; the last block also writes out[n].
+__global__ void scan_apply(const int* __restrict__ in, const int* __restrict__ boff, int* __restrict__ out, int64_t n) {
+  __shared__ int total;
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
+  int off = block_exclusive_scan(s, &total) + (boff ? boff[blockIdx.x] : 0);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) out[base + i] = off;
+    off += v[i];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = off;
+}
+
+int64_t scan_ws_ints(int64_t n) {
+  int64_t tot = 0;
+  while (n > SCAN_TILE) {
+    int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    tot += 2 * (nb + 1);
+    n = nb;
+  }
+  return tot + 2;
+}
+
+// exclusive scan of in[0..n) into out[0..n] (n+1 outputs).  in may alias out only if n <= SCAN_TILE... never aliased here.
+void exclusive_scan(const int* in, int* out, int64_t n, int* ws, cudaStream_t st) {
+  int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb <= 1) {
+    scan_apply<<<1, SCAN_THREADS, 0, st>>>(in, nullptr, out, n);
+    return;
+  }
+  int* bsum = ws;
+  int* bscan = ws + (nb + 1);
+  scan_block_sums<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, bsum, n);
+  exclusive_scan(bsum, bscan, nb, ws + 2 * (nb + 1), st);
+  scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, bscan, out, n);
+}
+
+__device__ __forceinline__ bool norm_index(int64_t v, int n, int* out) {
+  if (v < 0) v += n;  // torch advanced indexing wraps negatives
+  if (v < 0 || v >= n) return false;
+  *out = (int)v;
+  return true;
+}
+
+__global__ void fill_i32(int* p, int v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void count_rows(const int64_t* __restrict__ ei, int64_t E, int n, int* __restrict__ cnt, int* __restrict__ status) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int r, c;
+  if (norm_index(ei[e], n, &r) && norm_index(ei[E + e], n, &c)) atomicAdd(&cnt[r], 1);
+  else *status = 1;
+}
+
+// bucket layout: position off[r] holds the self loop, the rest is filled through cursor[r] (starts at 1)
+__global__ void place_self_loops(const int* __restrict__ off, int* __restrict__ bucket, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bucket[off[i]] = i;
+}
+
+__global__ void scatter_edges(const int64_t* __restrict__ ei, int64_t E, int n, const int* __restrict__ off,
+                              int* __restrict__ cursor, int* __restrict__ bucket) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int r, c;
+  if (norm_index(ei[e], n, &r) && norm_index(ei[E + e], n, &c)) {
+    int p = atomicAdd(&cursor[r], 1);
+    bucket[off[r] + p] = c;
+  }
+}
+
+// ---- per-segment rank sort.  UNIQUE: keep the first of each run of equal keys and pack them
+// at the segment start (count -> ucount[seg]); otherwise a stable full sort with a payload.
+constexpr int SORT_SMEM_KEYS = 8192;
+
+template <bool UNIQUE, bool PAYLOAD>
+__global__ void seg_sort_warp(const int* __restrict__ off, const int* __restrict__ kin, const int* __restrict__ pin,
+                              int* __restrict__ kout, int* __restrict__ pout, int* __restrict__ ucount, int nseg) {
+  int seg = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (seg >= nseg) return;
+  int b = off[seg], len = off[seg + 1] - b;
+  if (len > 32) return;  // handled by seg_sort_block
+  int key = lane < len ? kin[b + lane] : 0x7fffffff;
+  int pay = 0;
+  if (PAYLOAD) pay = lane < len ? pin[b + lane] : 0;
+  if (UNIQUE) {
+    bool first = lane < len;
+    for (int j = 0; j < len; ++j) {
+      int kj = __shfl_sync(FULL_MASK, key, j);
+      if (kj == key && j < lane) first = false;
+    }
+    unsigned fm = __ballot_sync(FULL_MASK, first);
+    int urank = 0;
+    for (int j = 0; j < len; ++j) {
+      int kj = __shfl_sync(FULL_MASK, key, j);
+      if (((fm >> j) & 1u) && kj < key) ++urank;
+    }
+    if (first) kout[b + urank] = key;
+    if (lane == 0) ucount[seg] = __popc(fm);
+  } else {
+    int rank = 0;
+    for (int j = 0; j < len; ++j) {
+      int kj = __shfl_sync(FULL_MASK, key, j);
+      if (kj < key || (kj == key && j < lane)) ++rank;
+    }
+    if (lane < len) {
+      kout[b + rank] = key;
+      if (PAYLOAD) pout[b + rank] = pay;
+    }
+  }
+}
+
+template <bool UNIQUE, bool PAYLOAD>
+__global__ void seg_sort_block(const int* __restrict__ off, const int* __restrict__ kin, const int* __restrict__ pin,
+                               int* __restrict__ kout, int* __restrict__ pout, int* __restrict__ ucount, int nseg) {
+  __shared__ int skey[SORT_SMEM_KEYS];
+  __shared__ int scount;
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    int b = off[seg], len = off[seg + 1] - b;
+    if (len <= 32) continue;
+    const bool in_smem = len <= SORT_SMEM_KEYS;
+    __syncthreads();
+    if (in_smem)
+      for (int i = threadIdx.x; i < len; i += blockDim.x) skey[i] = kin[b + i];
+    if (threadIdx.x == 0) scount = 0;
+    __syncthreads();
+    const int* keys = in_smem ? skey : (kin + b);
+    int local_first = 0;
+    if (UNIQUE) {
+      // phase 1: first-occurrence flags (scratch lives in pout); phase 2: rank among distinct keys
+      for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        int key = keys[i];
+        int first = 1;
+        for (int j = 0; j < i; ++j)
+          if (keys[j] == key) { first = 0; break; }
+        pout[b + i] = first;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        if (!pout[b + i]) continue;
+        int key = keys[i];
+        int urank = 0;
+        for (int j = 0; j < len; ++j) urank += (keys[j] < key) & pout[b + j];
+        kout[b + urank] = key;
+        ++local_first;
+      }
+    } else {
+      for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        int key = keys[i];
+        int rank = 0;
+        for (int j = 0; j < len; ++j) {
+          int kj = keys[j];
+          if (kj < key || (kj == key && j < i)) ++rank;
+        }
+        kout[b + rank] = key;
+        if (PAYLOAD) pout[b + rank] = pin[b + i];
+      }
+    }
+    if (UNIQUE) {
+      atomicAdd(&scount, local_first);
+      __syncthreads();
+      if (threadIdx.x == 0) ucount[seg] = scount;
+    }
+  }
+}
+
+// copy the packed unique keys of each row to their final place; also emit the row of every entry
+__global__ void compact_rows(const int* __restrict__ off, const int* __restrict__ rowptr, const int* __restrict__ staged,
+                             int* __restrict__ col, int* __restrict__ row, int n) {
+  int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  int src = off[r], dst = rowptr[r], len = rowptr[r + 1] - dst;
+  for (int i = lane; i < len; i += 32) {
+    col[dst + i] = staged[src + i];
+    row[dst + i] = r;
+  }
+}
+
+__global__ void count_cols(const int* __restrict__ rowptr, const int* __restrict__ col, int n, int* __restrict__ cnt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rowptr[n]) atomicAdd(&cnt[col[i]], 1);
+}
+
+__global__ void scatter_cols(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ row, int n,
+                             const int* __restrict__ off_t, int* __restrict__ cursor, int* __restrict__ brow, int* __restrict__ bperm) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rowptr[n]) return;
+  int c = col[i];
+  int p = off_t[c] + atomicAdd(&cursor[c], 1);
+  brow[p] = row[i];
+  bperm[p] = (int)i;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t cnt, off, cursor, bucket, staged, flags, ucount, scan, total;
+};
+WsLayout ws_layout(int64_t E, int32_t N) {
+  WsLayout L;
+  size_t p = 0;
+  int64_t tot = E + N;
+  auto take = [&](int64_t ints) { size_t o = p; p = align_up(p + (size_t)ints * 4, 256); return o; };
+  L.cnt = take(N + 1);
+  L.off = take(N + 1);
+  L.cursor = take(N + 1);
+  L.bucket = take(tot + 1);
+  L.staged = take(tot + 1);
+  L.flags = take(tot + 1);
+  L.ucount = take(N + 1);
+  L.scan = take(scan_ws_ints(tot > N ? tot : N) + scan_ws_ints(N + 1) + 16);
+  L.total = p;
+  return L;
+}
+
+}  // namespace
+
+TAGAN_API size_t tagan_csr_workspace_bytes(int64_t num_edges, int32_t num_nodes) {
+  if (num_edges < 0 || num_nodes < 0) return 0;
+  return ws_layout(num_edges, num_nodes).total;
+}
+
+TAGAN_API int tagan_csr_build(const int64_t* edge_index, int64_t E, int32_t N, int32_t* rowptr, int32_t* col,
+                              int32_t* row, int32_t* rowptr_t, int32_t* row_t, int32_t* perm_t, int32_t* status,
+                              void* workspace, size_t workspace_bytes, tagan_stream_t stream) {
+  if (E < 0 || N < 0 || !rowptr || !col || !row || !status || (E > 0 && !edge_index)) return TAGAN_E_INVALID;
+  if (E + (int64_t)N >= 0x7fffffffLL) return TAGAN_E_UNSUPPORTED;
+  const bool transpose = rowptr_t || row_t || perm_t;
+  if (transpose && !(rowptr_t && row_t && perm_t)) return TAGAN_E_INVALID;
+  WsLayout L = ws_layout(E, N);
+  if (!workspace || workspace_bytes < L.total) return TAGAN_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  char* w = static_cast<char*>(workspace);
+  int* cnt = (int*)(w + L.cnt);
+  int* off = (int*)(w + L.off);
+  int* cursor = (int*)(w + L.cursor);
+  int* bucket = (int*)(w + L.bucket);
+  int* staged = (int*)(w + L.staged);
+  int* flags = (int*)(w + L.flags);
+  int* ucount = (int*)(w + L.ucount);
+  int* scanws = (int*)(w + L.scan);
+  const int TB = 256;
+  cudaMemsetAsync(status, 0, sizeof(int), st);
+  if (N == 0) {
+    cudaMemsetAsync(rowptr, 0, sizeof(int), st);
+    if (transpose) cudaMemsetAsync(rowptr_t, 0, sizeof(int), st);
+    if (E > 0) fill_i32<<<1, 1, 0, st>>>(status, 1, 1);
+    return tagan_launch_status();
+  }
+  const unsigned gN = ceil_div_i64(N, TB), gE = ceil_div_i64(E > 0 ? E : 1, TB);
+  const unsigned gW = ceil_div_i64((int64_t)N * 32, TB);
+  const unsigned gHeavy = 148 * 4;
+
+  fill_i32<<<gN, TB, 0, st>>>(cnt, 1, N);         // one self loop per row
+  fill_i32<<<gN, TB, 0, st>>>(cursor, 1, N);
+  if (E > 0) count_rows<<<gE, TB, 0, st>>>(edge_index, E, N, cnt, status);
+  exclusive_scan(cnt, off, N, scanws, st);
+  place_self_loops<<<gN, TB, 0, st>>>(off, bucket, N);
+  if (E > 0) scatter_edges<<<gE, TB, 0, st>>>(edge_index, E, N, off, cursor, bucket);
+  seg_sort_warp<true, false><<<gW, TB, 0, st>>>(off, bucket, nullptr, staged, nullptr, ucount, N);
+  seg_sort_block<true, false><<<gHeavy, TB, 0, st>>>(off, bucket, nullptr, staged, flags, ucount, N);
+  exclusive_scan(ucount, rowptr, N, scanws, st);
+  compact_rows<<<gW, TB, 0, st>>>(off, rowptr, staged, col, row, N);
+
+  if (transpose) {
+    const unsigned gT = ceil_div_i64(E + N, TB);
+    cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)N, st);
+    cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)N, st);
+    count_cols<<<gT, TB, 0, st>>>(rowptr, col, N, cnt);
+    exclusive_scan(cnt, rowptr_t, N, scanws, st);
+    scatter_cols<<<gT, TB, 0, st>>>(rowptr, col, row, N, rowptr_t, cursor, bucket, staged);
+    seg_sort_warp<false, true><<<gW, TB, 0, st>>>(rowptr_t, bucket, staged, row_t, perm_t, nullptr, N);
+    seg_sort_block<false, true><<<gHeavy, TB, 0, st>>>(rowptr_t, bucket, staged, row_t, perm_t, nullptr, N);
+  }
+  return tagan_launch_status();
+}

@@ -1,0 +1,25 @@
+// tagan_gemm: precision dispatch between the fp32 FFMA path (gemm_simt.cu) and the tcgen05
+// tensor-core path (gemm_tc.cu).
+#include "common.cuh"
+
+size_t tagan_gemm_simt_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k);
+int tagan_gemm_simt(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                    int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+
+TAGAN_API size_t tagan_gemm_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k) {
+  if (op < 0 || op > 2 || m < 0 || n < 0 || k < 0) return 0;
+  return tagan_gemm_simt_workspace_bytes(op, m, n, k);
+}
+
+TAGAN_API int tagan_gemm(int32_t op, int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* B,
+                         int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t precision,
+                         void* workspace, size_t workspace_bytes, tagan_stream_t stream) {
+  if (op < 0 || op > 2 || m < 0 || n < 0 || k < 0 || !C || (k > 0 && (!A || !B))) return TAGAN_E_INVALID;
+  if (precision < 0 || precision > 2) return TAGAN_E_INVALID;
+  if (m == 0 || n == 0) return 0;
+  return tagan_gemm_simt(op, m, n, k, A, lda, B, ldb, bias, C, ldc, accumulate, workspace, workspace_bytes,
+                         as_stream(stream));
+}
+
+TAGAN_API int tagan_abi_version(void) { return 1; }

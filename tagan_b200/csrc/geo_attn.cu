@@ -1,0 +1,475 @@
+// (a2-a4) Fused geometric attention over a destination-sorted CSR.
+// Replaces GeometricAttention._get_attention_weights + `attn @ v` of the reference
+// (src/tagan/layers/geometric_attention.py:332-516, :579), which materialises [1,h,N,N].
+//
+// Layout: one warp per destination row.  A row of H floats is spread over the warp as NCHUNK
+// chunks of 32*VEC floats, lane l owning VEC contiguous floats of each chunk, so every gather
+// of a K/V/Q/dCtx row is NCHUNK fully coalesced 128-bit (VEC=4) warp loads.  A head of D floats
+// is owned by `group = D/VEC` adjacent lanes; per-head dot products are xor-shuffle reductions
+// over the group.  Softmax is online (running max / sum per head in registers); nothing is
+// accumulated with atomics.  Backward recomputes the scores: a row pass over the CSR produces
+// dQ and delta = dctx.ctx, a column pass over the transposed CSR produces dK and dV.
+//
+// HBM-bound: algorithmic bytes are nnz*(2*H*4+4) + N*(2*H*4+8h+8) forward.
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+
+template <int METRIC> struct MetricTraits {
+  static constexpr bool kDot = METRIC == TAGAN_METRIC_SCALED_DOT || METRIC == TAGAN_METRIC_DOT;
+  static constexpr bool kCos = METRIC == TAGAN_METRIC_COSINE_SIM || METRIC == TAGAN_METRIC_COSINE_DIST;
+  static constexpr bool kManhattan = METRIC == TAGAN_METRIC_MANHATTAN;
+  static constexpr bool kParam = METRIC == TAGAN_METRIC_GAUSSIAN || METRIC == TAGAN_METRIC_RBF;
+};
+
+// Per-(entry, head) score and the partial sums its backward needs.
+//   p1: q.k (dot/cos) | sum (q-k)^2 (sq family) | sum |q-k| (manhattan);  p2: k.k (cos only)
+template <int METRIC, int VEC>
+__device__ __forceinline__ float score_from_vectors(const float* q, const float* k, int group, float par, float qnorm,
+                                                    float& p1, float& p2) {
+  using MT = MetricTraits<METRIC>;
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (MT::kDot) a = fmaf(q[i], k[i], a);
+    else if (MT::kCos) { a = fmaf(q[i], k[i], a); b = fmaf(k[i], k[i], b); }
+    else if (MT::kManhattan) a += fabsf(q[i] - k[i]);
+    else { float d = q[i] - k[i]; a = fmaf(d, d, a); }
+  }
+  a = group_sum(a, group);
+  if (MT::kCos) b = group_sum(b, group);
+  p1 = a; p2 = b;
+  if (METRIC == TAGAN_METRIC_SCALED_DOT) return a * par;            // par = 1/sqrt(D)
+  if (METRIC == TAGAN_METRIC_DOT) return a;
+  if (MT::kCos) {
+    float kn = sqrtf(b);
+    kn = kn == 0.f ? 1e-8f : kn;
+    float u = a / (qnorm * kn);
+    u = fminf(fmaxf(u, -1.f), 1.f);
+    return METRIC == TAGAN_METRIC_COSINE_SIM ? u : -(1.f - u);
+  }
+  if (METRIC == TAGAN_METRIC_EUCLIDEAN) return -sqrtf(a + 1e-8f);
+  if (METRIC == TAGAN_METRIC_SQ_EUCLIDEAN) return -a;
+  if (METRIC == TAGAN_METRIC_MANHATTAN) return -a;
+  if (METRIC == TAGAN_METRIC_GAUSSIAN) return expf(-a / (2.f * par * par));   // par = sigma
+  return expf(-par * a);                                                       // rbf, par = gamma
+}
+
+// out += g * d(score)/d(q)  (WRT_Q) or g * d(score)/d(k); returns g * d(score)/d(param).
+template <int METRIC, int VEC, bool WRT_Q>
+__device__ __forceinline__ float accum_score_grad(float g, const float* q, const float* k, float s, float p1, float p2,
+                                                  float par, float qnorm, float* out) {
+  using MT = MetricTraits<METRIC>;
+  if (MT::kDot) {
+    float c = METRIC == TAGAN_METRIC_SCALED_DOT ? g * par : g;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) out[i] = fmaf(c, WRT_Q ? k[i] : q[i], out[i]);
+    return 0.f;
+  }
+  if (MT::kCos) {
+    float kn = sqrtf(p2);
+    const bool kzero = kn == 0.f;
+    kn = kzero ? 1e-8f : kn;
+    float inv = 1.f / (qnorm * kn);
+    float u = p1 * inv;
+    float gg = (u >= -1.f && u <= 1.f) ? g : 0.f;   // clamp passes gradient on the closed interval
+    float self_c;
+    if (WRT_Q) self_c = (qnorm == 1e-8f) ? 0.f : -gg * u / (qnorm * qnorm);
+    else self_c = kzero ? 0.f : -gg * u / (kn * kn);
+    float cross_c = gg * inv;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float self_v = WRT_Q ? q[i] : k[i];
+      float cross_v = WRT_Q ? k[i] : q[i];
+      out[i] = fmaf(cross_c, cross_v, fmaf(self_c, self_v, out[i]));
+    }
+    return 0.f;
+  }
+  if (MT::kManhattan) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float d = q[i] - k[i];
+      float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      out[i] += (WRT_Q ? -g : g) * sg;
+    }
+    return 0.f;
+  }
+  // squared-distance family: d(score)/dq = coef * (q - k), d/dk = -coef * (q - k)
+  float coef, dpar = 0.f;
+  if (METRIC == TAGAN_METRIC_EUCLIDEAN) coef = g / s;                 // s = -sqrt(sq+eps)
+  else if (METRIC == TAGAN_METRIC_SQ_EUCLIDEAN) coef = -2.f * g;
+  else if (METRIC == TAGAN_METRIC_GAUSSIAN) {
+    float is2 = 1.f / (par * par);
+    coef = -g * s * is2;
+    dpar = g * s * p1 * is2 / par;
+  } else {
+    coef = -2.f * par * g * s;
+    dpar = -g * p1 * s;
+  }
+  if (!WRT_Q) coef = -coef;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) out[i] = fmaf(coef, q[i] - k[i], out[i]);
+  return dpar;
+}
+
+template <int METRIC>
+__device__ __forceinline__ float head_param(const float* metric_param, int head, int D) {
+  if (METRIC == TAGAN_METRIC_SCALED_DOT) return 1.f / sqrtf((float)D);
+  if (MetricTraits<METRIC>::kParam) return metric_param ? __ldg(metric_param + head) : 1.f;
+  return 0.f;
+}
+
+template <int VEC, int NCHUNK>
+__device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const float* base, int lane) {
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) VecIO<VEC>::load(dst[c], base + c * 32 * VEC + lane * VEC);
+}
+
+template <int METRIC, int VEC, int NCHUNK>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+geo_attn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+                    const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
+                    const float* __restrict__ metric_param, float* __restrict__ ctx, float* __restrict__ lse,
+                    float* __restrict__ attn) {
+  constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
+  constexpr int H = 32 * VEC * NCHUNK;
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const int group = D / VEC;
+  float q[NCHUNK][VEC], acc[NCHUNK][VEC], m[NCHUNK], l[NCHUNK], par[NCHUNK], qn[NCHUNK];
+  int head[NCHUNK];
+  load_row<VEC, NCHUNK>(q, Q + (int64_t)row * ld, lane);
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    head[c] = (c * 32 * VEC + lane * VEC) / D;
+    par[c] = head_param<METRIC>(metric_param, head[c], D);
+    m[c] = -INFINITY; l[c] = 0.f; qn[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[c][i] = 0.f;
+    if (MetricTraits<METRIC>::kCos) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) t = fmaf(q[c][i], q[c][i], t);
+      t = sqrtf(group_sum(t, group));
+      qn[c] = t == 0.f ? 1e-8f : t;
+    }
+  }
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  for (int base = beg; base < end; base += 32) {
+    const int n = min(32, end - base);
+    const int mycol = lane < n ? __ldg(col + base + lane) : 0;
+    for (int j = 0; j < n; j += U) {
+      float kk[U][NCHUNK][VEC], vv[U][NCHUNK][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cj = __shfl_sync(FULL_MASK, mycol, min(j + u, n - 1));
+        load_row<VEC, NCHUNK>(kk[u], K + (int64_t)cj * ld, lane);
+        load_row<VEC, NCHUNK>(vv[u], V + (int64_t)cj * ld, lane);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j + u < n) {
+#pragma unroll
+          for (int c = 0; c < NCHUNK; ++c) {
+            float p1, p2;
+            const float s = score_from_vectors<METRIC, VEC>(q[c], kk[u][c], group, par[c], qn[c], p1, p2);
+            const float mn = fmaxf(m[c], s);
+            const float sc = __expf(m[c] - mn);
+            const float p = __expf(s - mn);
+            l[c] = fmaf(l[c], sc, p);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[c][i] = fmaf(acc[c][i], sc, p * vv[u][c][i]);
+            m[c] = mn;
+          }
+        }
+      }
+    }
+  }
+  float lse_c[NCHUNK];
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    const float inv = 1.f / l[c];
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = acc[c][i] * inv;
+    VecIO<VEC>::store(ctx + (int64_t)row * H + c * 32 * VEC + lane * VEC, o);
+    lse_c[c] = m[c] + logf(l[c]);
+    if ((lane & (group - 1)) == 0) lse[(int64_t)row * heads + head[c]] = lse_c[c];   // group leader
+  }
+  if (attn != nullptr) {   // optional second pass: per-entry softmax weights
+    for (int e = beg; e < end; ++e) {
+      const int cj = __ldg(col + e);
+      float kr[NCHUNK][VEC];
+      load_row<VEC, NCHUNK>(kr, K + (int64_t)cj * ld, lane);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        float p1, p2;
+        const float s = score_from_vectors<METRIC, VEC>(q[c], kr[c], group, par[c], qn[c], p1, p2);
+        if ((lane & (group - 1)) == 0) attn[(int64_t)e * heads + head[c]] = __expf(s - lse_c[c]);
+      }
+    }
+  }
+}
+
+// Row pass: dQ[i] = sum_e ds_e * dscore/dq, delta[i,h] = dctx_i . ctx_i, optional dparam partials.
+template <int METRIC, int VEC, int NCHUNK>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+geo_attn_bwd_row_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+                        const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
+                        const float* __restrict__ metric_param, const float* __restrict__ ctx,
+                        const float* __restrict__ lse, const float* __restrict__ dctx, float* __restrict__ dQ,
+                        int64_t ldd, float* __restrict__ delta, float* __restrict__ dparam_rows) {
+  constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
+  constexpr int H = 32 * VEC * NCHUNK;
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const int group = D / VEC;
+  float q[NCHUNK][VEC], go[NCHUNK][VEC], dq[NCHUNK][VEC], par[NCHUNK], qn[NCHUNK], ls[NCHUNK], dl[NCHUNK], dpar[NCHUNK];
+  int head[NCHUNK];
+  load_row<VEC, NCHUNK>(q, Q + (int64_t)row * ld, lane);
+  load_row<VEC, NCHUNK>(go, dctx + (int64_t)row * H, lane);
+  {
+    float cx[NCHUNK][VEC];
+    load_row<VEC, NCHUNK>(cx, ctx + (int64_t)row * H, lane);
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) t = fmaf(go[c][i], cx[c][i], t);
+      dl[c] = group_sum(t, group);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    head[c] = (c * 32 * VEC + lane * VEC) / D;
+    par[c] = head_param<METRIC>(metric_param, head[c], D);
+    ls[c] = __ldg(lse + (int64_t)row * heads + head[c]);
+    dpar[c] = 0.f; qn[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dq[c][i] = 0.f;
+    if (MetricTraits<METRIC>::kCos) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) t = fmaf(q[c][i], q[c][i], t);
+      t = sqrtf(group_sum(t, group));
+      qn[c] = t == 0.f ? 1e-8f : t;
+    }
+    if ((lane & (group - 1)) == 0) delta[(int64_t)row * heads + head[c]] = dl[c];
+  }
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  for (int base = beg; base < end; base += 32) {
+    const int n = min(32, end - base);
+    const int mycol = lane < n ? __ldg(col + base + lane) : 0;
+    for (int j = 0; j < n; j += U) {
+      float kk[U][NCHUNK][VEC], vv[U][NCHUNK][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cj = __shfl_sync(FULL_MASK, mycol, min(j + u, n - 1));
+        load_row<VEC, NCHUNK>(kk[u], K + (int64_t)cj * ld, lane);
+        load_row<VEC, NCHUNK>(vv[u], V + (int64_t)cj * ld, lane);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j + u < n) {
+#pragma unroll
+          for (int c = 0; c < NCHUNK; ++c) {
+            float p1, p2;
+            const float s = score_from_vectors<METRIC, VEC>(q[c], kk[u][c], group, par[c], qn[c], p1, p2);
+            const float a = __expf(s - ls[c]);
+            float dp = 0.f;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dp = fmaf(go[c][i], vv[u][c][i], dp);
+            dp = group_sum(dp, group);
+            const float ds = a * (dp - dl[c]);
+            dpar[c] += accum_score_grad<METRIC, VEC, true>(ds, q[c], kk[u][c], s, p1, p2, par[c], qn[c], dq[c]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    VecIO<VEC>::store(dQ + (int64_t)row * ldd + c * 32 * VEC + lane * VEC, dq[c]);
+    if (MetricTraits<METRIC>::kParam && dparam_rows != nullptr && (lane & (group - 1)) == 0)
+      dparam_rows[(int64_t)row * heads + head[c]] = dpar[c];
+  }
+}
+
+// Column pass over the transposed CSR: for source node j, dV[j] = sum_e a_e dctx[row_e],
+// dK[j] = sum_e ds_e * dscore/dk.  Gathers Q[row], dctx[row], lse[row,h], delta[row,h].
+template <int METRIC, int VEC, int NCHUNK>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+geo_attn_bwd_col_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+                        const int* __restrict__ rowptr_t, const int* __restrict__ row_t, int N, int heads, int D,
+                        const float* __restrict__ metric_param, const float* __restrict__ lse,
+                        const float* __restrict__ delta, const float* __restrict__ dctx, float* __restrict__ dK,
+                        float* __restrict__ dV, int64_t ldd) {
+  constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
+  constexpr int H = 32 * VEC * NCHUNK;
+  const int node = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (node >= N) return;
+  const int group = D / VEC;
+  float k[NCHUNK][VEC], v[NCHUNK][VEC], dk[NCHUNK][VEC], dv[NCHUNK][VEC], par[NCHUNK];
+  int head[NCHUNK];
+  load_row<VEC, NCHUNK>(k, K + (int64_t)node * ld, lane);
+  load_row<VEC, NCHUNK>(v, V + (int64_t)node * ld, lane);
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    head[c] = (c * 32 * VEC + lane * VEC) / D;
+    par[c] = head_param<METRIC>(metric_param, head[c], D);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { dk[c][i] = 0.f; dv[c][i] = 0.f; }
+  }
+  const int beg = rowptr_t[node], end = rowptr_t[node + 1];
+  for (int base = beg; base < end; base += 32) {
+    const int n = min(32, end - base);
+    const int myrow = lane < n ? __ldg(row_t + base + lane) : 0;
+    for (int j = 0; j < n; j += U) {
+      float qq[U][NCHUNK][VEC], gg[U][NCHUNK][VEC], ls[U][NCHUNK], dl[U][NCHUNK];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = __shfl_sync(FULL_MASK, myrow, min(j + u, n - 1));
+        load_row<VEC, NCHUNK>(qq[u], Q + (int64_t)r * ld, lane);
+        load_row<VEC, NCHUNK>(gg[u], dctx + (int64_t)r * H, lane);
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          ls[u][c] = __ldg(lse + (int64_t)r * heads + head[c]);
+          dl[u][c] = __ldg(delta + (int64_t)r * heads + head[c]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j + u < n) {
+#pragma unroll
+          for (int c = 0; c < NCHUNK; ++c) {
+            float qn = 0.f;
+            if (MetricTraits<METRIC>::kCos) {
+              float t = 0.f;
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) t = fmaf(qq[u][c][i], qq[u][c][i], t);
+              t = sqrtf(group_sum(t, group));
+              qn = t == 0.f ? 1e-8f : t;
+            }
+            float p1, p2;
+            const float s = score_from_vectors<METRIC, VEC>(qq[u][c], k[c], group, par[c], qn, p1, p2);
+            const float a = __expf(s - ls[u][c]);
+            float dp = 0.f;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              dv[c][i] = fmaf(a, gg[u][c][i], dv[c][i]);
+              dp = fmaf(gg[u][c][i], v[c][i], dp);
+            }
+            dp = group_sum(dp, group);
+            const float ds = a * (dp - dl[u][c]);
+            accum_score_grad<METRIC, VEC, false>(ds, qq[u][c], k[c], s, p1, p2, par[c], qn, dk[c]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    VecIO<VEC>::store(dK + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dk[c]);
+    VecIO<VEC>::store(dV + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dv[c]);
+  }
+}
+
+// dparam[h] = sum over rows of dparam_rows[row,h]; one block per head, fixed-order tree.
+__global__ void reduce_rows_per_head(const float* __restrict__ rows, int64_t n, int heads, float* __restrict__ out) {
+  __shared__ float sm[256];
+  const int h = blockIdx.x;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) s += rows[i * heads + h];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[h] = sm[0];
+}
+
+struct Shape { int vec, nchunk; };
+bool pick_shape(int H, int heads, Shape* s) {
+  if (H <= 0 || heads <= 0 || H % heads) return false;
+  int vec, nchunk;
+  if (H == 32) { vec = 1; nchunk = 1; }
+  else if (H == 64) { vec = 2; nchunk = 1; }
+  else if (H == 128) { vec = 4; nchunk = 1; }
+  else if (H == 256) { vec = 4; nchunk = 2; }
+  else if (H == 512) { vec = 4; nchunk = 4; }
+  else return false;
+  int D = H / heads;
+  if (D % vec) return false;
+  int group = D / vec;
+  if (group < 1 || group > 32 || (group & (group - 1))) return false;
+  s->vec = vec; s->nchunk = nchunk;
+  return true;
+}
+
+#define DISPATCH_SHAPE(METRIC, FN, ...)                                          \
+  if (sh.vec == 1 && sh.nchunk == 1) FN<METRIC, 1, 1> __VA_ARGS__;                \
+  else if (sh.vec == 2 && sh.nchunk == 1) FN<METRIC, 2, 1> __VA_ARGS__;           \
+  else if (sh.vec == 4 && sh.nchunk == 1) FN<METRIC, 4, 1> __VA_ARGS__;           \
+  else if (sh.vec == 4 && sh.nchunk == 2) FN<METRIC, 4, 2> __VA_ARGS__;           \
+  else FN<METRIC, 4, 4> __VA_ARGS__;
+
+#define DISPATCH_METRIC(FN, ...)                                                            \
+  switch (metric) {                                                                         \
+    case TAGAN_METRIC_SCALED_DOT: { DISPATCH_SHAPE(TAGAN_METRIC_SCALED_DOT, FN, __VA_ARGS__) } break;   \
+    case TAGAN_METRIC_DOT: { DISPATCH_SHAPE(TAGAN_METRIC_DOT, FN, __VA_ARGS__) } break;                 \
+    case TAGAN_METRIC_COSINE_SIM: { DISPATCH_SHAPE(TAGAN_METRIC_COSINE_SIM, FN, __VA_ARGS__) } break;   \
+    case TAGAN_METRIC_EUCLIDEAN: { DISPATCH_SHAPE(TAGAN_METRIC_EUCLIDEAN, FN, __VA_ARGS__) } break;     \
+    case TAGAN_METRIC_SQ_EUCLIDEAN: { DISPATCH_SHAPE(TAGAN_METRIC_SQ_EUCLIDEAN, FN, __VA_ARGS__) } break; \
+    case TAGAN_METRIC_MANHATTAN: { DISPATCH_SHAPE(TAGAN_METRIC_MANHATTAN, FN, __VA_ARGS__) } break;     \
+    case TAGAN_METRIC_COSINE_DIST: { DISPATCH_SHAPE(TAGAN_METRIC_COSINE_DIST, FN, __VA_ARGS__) } break; \
+    case TAGAN_METRIC_GAUSSIAN: { DISPATCH_SHAPE(TAGAN_METRIC_GAUSSIAN, FN, __VA_ARGS__) } break;       \
+    case TAGAN_METRIC_RBF: { DISPATCH_SHAPE(TAGAN_METRIC_RBF, FN, __VA_ARGS__) } break;                 \
+    default: return TAGAN_E_INVALID;                                                        \
+  }
+
+}  // namespace
+
+TAGAN_API int tagan_geo_attn_fwd(const float* Q, const float* K, const float* V, int64_t ld, const int32_t* rowptr,
+                                 const int32_t* col, int32_t N, int32_t H, int32_t heads, int32_t metric,
+                                 const float* metric_param, float* ctx, float* lse, float* attn,
+                                 tagan_stream_t stream) {
+  if (!Q || !K || !V || !rowptr || !col || !ctx || !lse || N < 0 || ld < H) return TAGAN_E_INVALID;
+  Shape sh;
+  if (!pick_shape(H, heads, &sh) || (ld % sh.vec)) return TAGAN_E_UNSUPPORTED;
+  if (N == 0) return 0;
+  const int D = H / heads;
+  dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_METRIC(geo_attn_fwd_kernel, <<<grid, block, 0, st>>>(Q, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, attn))
+  return tagan_launch_status();
+}
+
+TAGAN_API int tagan_geo_attn_bwd(const float* Q, const float* K, const float* V, int64_t ld, const int32_t* rowptr,
+                                 const int32_t* col, const int32_t* rowptr_t, const int32_t* row_t, int32_t N,
+                                 int32_t H, int32_t heads, int32_t metric, const float* metric_param,
+                                 const float* ctx, const float* lse, const float* dctx, float* dQ, float* dK,
+                                 float* dV, int64_t ldd, float* delta_ws, float* dparam_ws, float* dparam,
+                                 tagan_stream_t stream) {
+  if (!Q || !K || !V || !rowptr || !col || !rowptr_t || !row_t || !ctx || !lse || !dctx || !dQ || !dK || !dV ||
+      !delta_ws || N < 0 || ld < H || ldd < H)
+    return TAGAN_E_INVALID;
+  Shape sh;
+  if (!pick_shape(H, heads, &sh) || (ld % sh.vec) || (ldd % sh.vec)) return TAGAN_E_UNSUPPORTED;
+  const bool want_dparam = metric_param != nullptr && (metric == TAGAN_METRIC_GAUSSIAN || metric == TAGAN_METRIC_RBF);
+  if (want_dparam && (!dparam_ws || !dparam)) return TAGAN_E_INVALID;
+  if (N == 0) return 0;
+  const int D = H / heads;
+  dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
+  cudaStream_t st = as_stream(stream);
+  float* dpr = want_dparam ? dparam_ws : nullptr;
+  DISPATCH_METRIC(geo_attn_bwd_row_kernel, <<<grid, block, 0, st>>>(Q, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, dctx, dQ, ldd, delta_ws, dpr))
+  DISPATCH_METRIC(geo_attn_bwd_col_kernel, <<<grid, block, 0, st>>>(Q, K, V, ld, rowptr_t, row_t, N, heads, D, metric_param, lse, delta_ws, dctx, dK, dV, ldd))
+  if (want_dparam) reduce_rows_per_head<<<heads, 256, 0, st>>>(dparam_ws, N, heads, dparam);
+  return tagan_launch_status();
+}

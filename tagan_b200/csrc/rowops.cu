@@ -1,0 +1,294 @@
+// Row-wise building blocks: LayerNorm (eps 1e-5, biased variance, as nn.LayerNorm) forward /
+// backward with fused residual add and per-row scale, deterministic column sums (bias and
+// LayerNorm-affine gradients), and small fused element-wise ops.  All HBM-bound streams:
+// one warp per row; rows are re-read from L1 rather than held in registers so any width works.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_WARPS = 8;
+constexpr int MAX_LN_COLS = 512;
+constexpr float LN_EPS = 1e-5f;
+
+// y = ((x+res) - mean) * rstd * gamma + beta, optionally * rowscale[row].
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ res, int64_t ldres,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ rowscale, float* __restrict__ y, int64_t ldy,
+                     float* __restrict__ sum_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     int64_t rows, int cols) {
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  const float* rr = res ? res + row * ldres : nullptr;
+  float* yr = y + row * ldy;
+  float* sr = sum_out ? sum_out + row * (int64_t)cols : nullptr;
+  const float rs = rowscale ? rowscale[row] : 1.f;
+  if (gamma == nullptr) {   // use_layer_norm = False: y = (x + res) * rowscale
+    for (int c = lane; c < cols; c += 32) {
+      float v = rr ? xr[c] + rr[c] : xr[c];
+      if (sr) sr[c] = v;
+      yr[c] = v * rs;
+    }
+    return;
+  }
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    float v = rr ? xr[c] + rr[c] : xr[c];
+    if (sr) sr[c] = v;
+    s += v;
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float q = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    float v = (rr ? xr[c] + rr[c] : xr[c]) - mean;
+    q = fmaf(v, v, q);
+  }
+  const float rstd = 1.f / sqrtf(warp_sum(q) / (float)cols + LN_EPS);
+  for (int c = lane; c < cols; c += 32) {
+    float v = (rr ? xr[c] + rr[c] : xr[c]);
+    yr[c] = ((v - mean) * rstd * gamma[c] + beta[c]) * rs;
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*rowscale*gamma; per-block partial
+// dgamma/dbeta accumulated in a fixed order (rows ascending inside a warp, warps summed in order).
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ xsum, int64_t ldx,
+                     const float* __restrict__ gamma, const float* __restrict__ rowscale,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
+                     int64_t lddx, int accumulate, float* __restrict__ partial /*[parts][2][cols]*/,
+                     int64_t rows, int cols, int64_t rows_per_block) {
+  __shared__ float acc[LN_WARPS][2][MAX_LN_COLS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = lane; c < cols; c += 32) { acc[w][0][c] = 0.f; acc[w][1][c] = 0.f; }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  for (int64_t row = r0 + w; row < r1; row += LN_WARPS) {
+    const float* dyr = dy + row * lddy;
+    float* dxr = dx + row * lddx;
+    const float rs = rowscale ? rowscale[row] : 1.f;
+    if (gamma == nullptr) {
+      for (int c = lane; c < cols; c += 32) {
+        float g = dyr[c] * rs;
+        dxr[c] = accumulate ? dxr[c] + g : g;
+      }
+      continue;
+    }
+    const float* xr = xsum + row * ldx;
+    const float mu = mean[row], rsd = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      float d = dyr[c] * rs;
+      float xh = (xr[c] - mu) * rsd;
+      float g = d * gamma[c];
+      s1 += g;
+      s2 = fmaf(g, xh, s2);
+      acc[w][0][c] = fmaf(d, xh, acc[w][0][c]);
+      acc[w][1][c] += d;
+    }
+    s1 = warp_sum(s1) / (float)cols;
+    s2 = warp_sum(s2) / (float)cols;
+    for (int c = lane; c < cols; c += 32) {
+      float xh = (xr[c] - mu) * rsd;
+      float g = dyr[c] * rs * gamma[c];
+      float v = rsd * (g - s1 - xh * s2);
+      dxr[c] = accumulate ? dxr[c] + v : v;
+    }
+  }
+  __syncthreads();
+  if (partial != nullptr && gamma != nullptr) {
+    for (int c = threadIdx.x; c < cols; c += LN_WARPS * 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int k = 0; k < LN_WARPS; ++k) { a += acc[k][0][c]; b += acc[k][1][c]; }
+      partial[((int64_t)blockIdx.x * 2 + 0) * cols + c] = a;
+      partial[((int64_t)blockIdx.x * 2 + 1) * cols + c] = b;
+    }
+  }
+}
+
+__global__ void reduce_partials2(const float* __restrict__ partial, int parts, int cols, float* __restrict__ out0,
+                                 float* __restrict__ out1) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float a = 0.f, b = 0.f;
+  for (int p = 0; p < parts; ++p) {
+    a += partial[((int64_t)p * 2 + 0) * cols + c];
+    b += partial[((int64_t)p * 2 + 1) * cols + c];
+  }
+  if (out0) out0[c] = a;
+  if (out1) out1[c] = b;
+}
+
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ partial, int64_t rows, int cols,
+                      int64_t rows_per_block) {
+  // thread t owns columns t, t+256, ...; rows walked in order -> deterministic
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += x[r * ldx + c];
+    partial[(int64_t)blockIdx.x * cols + c] = s;
+  }
+}
+__global__ void reduce_partials1(const float* __restrict__ partial, int parts, int cols, float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float a = 0.f;
+  for (int p = 0; p < parts; ++p) a += partial[(int64_t)p * cols + c];
+  out[c] = a;
+}
+
+int parts_for(int64_t rows) {
+  int64_t p = (rows + 63) / 64;
+  if (p > 592) p = 592;
+  if (p < 1) p = 1;
+  return (int)p;
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta,
+                             float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = alpha * a[i];
+  if (b) v = fmaf(beta, b[i], v);
+  out[i] = v;
+}
+
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  y[i] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+  dx[i] = dy[i] * (cdf + v * pdf);
+}
+
+__global__ void scale_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ rowscale,
+                                  float* __restrict__ y, int64_t ldy, int64_t rows, int cols, int accumulate) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  int64_t r = i / cols;
+  int c = (int)(i - r * cols);
+  float v = x[r * ldx + c] * (rowscale ? rowscale[r] : 1.f);
+  float* o = y + r * ldy + c;
+  *o = accumulate ? *o + v : v;
+}
+
+__global__ void decay_scale_kernel(const float* __restrict__ ts, int64_t ldts, int t, float* __restrict__ out, int64_t rows) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  float d = ts[i * ldts + t] - ts[i * ldts + t - 1];
+  d = fminf(fmaxf(d, 0.f), 10.f);
+  out[i] = expf(-d);
+}
+
+}  // namespace
+
+TAGAN_API int tagan_layernorm_fwd(const float* x, int64_t ldx, const float* res, int64_t ldres, const float* gamma,
+                                  const float* beta, const float* rowscale, float* y, int64_t ldy, float* sum_out,
+                                  float* mean, float* rstd, int64_t rows, int32_t cols, tagan_stream_t stream) {
+  if (!x || !y || rows < 0 || cols <= 0 || (gamma && !beta)) return TAGAN_E_INVALID;
+  if (rows == 0) return 0;
+  unsigned grid = ceil_div_i64(rows, LN_WARPS);
+  layernorm_fwd_kernel<<<grid, LN_WARPS * 32, 0, as_stream(stream)>>>(x, ldx, res, ldres, gamma, beta, rowscale, y, ldy,
+                                                                      sum_out, mean, rstd, rows, cols);
+  return tagan_launch_status();
+}
+
+TAGAN_API size_t tagan_layernorm_bwd_workspace_bytes(int64_t rows, int32_t cols) {
+  return (size_t)parts_for(rows) * 2 * (size_t)cols * sizeof(float);
+}
+
+TAGAN_API int tagan_layernorm_bwd(const float* dy, int64_t lddy, const float* xsum, int64_t ldx, const float* gamma,
+                                  const float* rowscale, const float* mean, const float* rstd, float* dx, int64_t lddx,
+                                  int32_t dx_accumulate, float* dgamma, float* dbeta, void* workspace,
+                                  size_t workspace_bytes, int64_t rows, int32_t cols, tagan_stream_t stream) {
+  if (!dy || !dx || rows < 0 || cols <= 0) return TAGAN_E_INVALID;
+  if (gamma && (!xsum || !mean || !rstd)) return TAGAN_E_INVALID;
+  if (cols > MAX_LN_COLS) return TAGAN_E_UNSUPPORTED;
+  const bool want_affine = gamma && (dgamma || dbeta);
+  if (want_affine && (!workspace || workspace_bytes < tagan_layernorm_bwd_workspace_bytes(rows, cols)))
+    return TAGAN_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  if (rows == 0) {
+    if (dgamma) cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, st);
+    if (dbeta) cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, st);
+    return 0;
+  }
+  const int parts = parts_for(rows);
+  const int64_t rpb = (rows + parts - 1) / parts;
+  layernorm_bwd_kernel<<<parts, LN_WARPS * 32, 0, st>>>(dy, lddy, xsum, ldx, gamma, rowscale, mean, rstd, dx, lddx,
+                                                        dx_accumulate, want_affine ? (float*)workspace : nullptr,
+                                                        rows, cols, rpb);
+  if (want_affine)
+    reduce_partials2<<<(cols + 127) / 128, 128, 0, st>>>((const float*)workspace, parts, cols, dgamma, dbeta);
+  return tagan_launch_status();
+}
+
+TAGAN_API size_t tagan_colsum_workspace_bytes(int64_t rows, int32_t cols) {
+  return (size_t)parts_for(rows) * (size_t)cols * sizeof(float);
+}
+
+TAGAN_API int tagan_colsum(const float* x, int64_t ldx, float* out, void* workspace, size_t workspace_bytes,
+                           int64_t rows, int32_t cols, tagan_stream_t stream) {
+  if (!x || !out || rows < 0 || cols <= 0) return TAGAN_E_INVALID;
+  if (!workspace || workspace_bytes < tagan_colsum_workspace_bytes(rows, cols)) return TAGAN_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  if (rows == 0) { cudaMemsetAsync(out, 0, sizeof(float) * cols, st); return 0; }
+  const int parts = parts_for(rows);
+  const int64_t rpb = (rows + parts - 1) / parts;
+  colsum_partial_kernel<<<parts, 256, 0, st>>>(x, ldx, (float*)workspace, rows, cols, rpb);
+  reduce_partials1<<<(cols + 127) / 128, 128, 0, st>>>((const float*)workspace, parts, cols, out);
+  return tagan_launch_status();
+}
+
+TAGAN_API int tagan_axpby(const float* a, float alpha, const float* b, float beta, float* out, int64_t n,
+                          tagan_stream_t stream) {
+  if (!a || !out || n < 0) return TAGAN_E_INVALID;
+  if (n == 0) return 0;
+  axpby_kernel<<<ceil_div_i64(n, 256), 256, 0, as_stream(stream)>>>(a, alpha, b, beta, out, n);
+  return tagan_launch_status();
+}
+
+TAGAN_API int tagan_gelu_fwd(const float* x, float* y, int64_t n, tagan_stream_t stream) {
+  if (!x || !y || n < 0) return TAGAN_E_INVALID;
+  if (n == 0) return 0;
+  gelu_fwd_kernel<<<ceil_div_i64(n, 256), 256, 0, as_stream(stream)>>>(x, y, n);
+  return tagan_launch_status();
+}
+TAGAN_API int tagan_gelu_bwd(const float* dy, const float* x, float* dx, int64_t n, tagan_stream_t stream) {
+  if (!dy || !x || !dx || n < 0) return TAGAN_E_INVALID;
+  if (n == 0) return 0;
+  gelu_bwd_kernel<<<ceil_div_i64(n, 256), 256, 0, as_stream(stream)>>>(dy, x, dx, n);
+  return tagan_launch_status();
+}
+
+TAGAN_API int tagan_scale_rows(const float* x, int64_t ldx, const float* rowscale, float* y, int64_t ldy,
+                               int64_t rows, int32_t cols, int32_t accumulate, tagan_stream_t stream) {
+  if (!x || !y || rows < 0 || cols <= 0) return TAGAN_E_INVALID;
+  if (rows == 0) return 0;
+  scale_rows_kernel<<<ceil_div_i64(rows * cols, 256), 256, 0, as_stream(stream)>>>(x, ldx, rowscale, y, ldy, rows, cols, accumulate);
+  return tagan_launch_status();
+}
+
+TAGAN_API int tagan_decay_scale(const float* ts, int64_t ldts, int32_t t, float* rowscale, int64_t rows,
+                                tagan_stream_t stream) {
+  if (!ts || !rowscale || rows < 0 || t < 1) return TAGAN_E_INVALID;
+  if (rows == 0) return 0;
+  decay_scale_kernel<<<ceil_div_i64(rows, 256), 256, 0, as_stream(stream)>>>(ts, ldts, t, rowscale, rows);
+  return tagan_launch_status();
+}

@@ -1,0 +1,351 @@
+"""Thin host wrappers over the C ABI plus the autograd glue.
+
+Each wrapper checks that tensors live on a CUDA device (no CPU fallback), hands raw pointers
+and torch's current stream to libtagan_b200.so and raises ``RuntimeError`` on a non-zero
+return code (SURVEY.md section 8b error convention).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+METRICS = ["scaled_dot_product", "dot_product", "cosine_similarity", "euclidean", "squared_euclidean",
+           "manhattan", "cosine_distance", "gaussian_kernel", "rbf_kernel"]
+METRIC_ID = {m: i for i, m in enumerate(METRICS)}
+
+# 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = 1xTF32 tcgen05
+GEMM_PRECISION = 0
+
+# number of libtagan_b200 kernel-launching calls made (bench.py reports launches from this)
+CALLS = {"n": 0}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("tagan_b200 has no CPU path: tensor must live on a CUDA device")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32, last dim contiguous."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() == 0 or t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _rows(t: torch.Tensor):
+    """View a [..., C] tensor as (rows, C, ld); copies only if rows are not uniformly strided."""
+    t = _f32c(t)
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.dim() > 2:
+        if not t.is_contiguous():
+            t = t.contiguous()
+        t = t.view(-1, t.shape[-1])
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else t.shape[1]
+    return t, t.shape[0], t.shape[1], ld
+
+
+_WS = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream); stream order makes reuse safe."""
+    key = (torch.device(device).index, torch.cuda.current_stream().cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+# ----------------------------------------------------------------------------------------
+# (a1) CSR
+# ----------------------------------------------------------------------------------------
+@dataclass
+class CSR:
+    num_nodes: int
+    num_edges: int
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    row: torch.Tensor
+    rowptr_t: Optional[torch.Tensor]
+    row_t: Optional[torch.Tensor]
+    perm_t: Optional[torch.Tensor]
+    status: torch.Tensor
+
+    @property
+    def nnz(self) -> int:          # host sync; only for tests / attention-weight export
+        return int(self.rowptr[-1].item())
+
+
+def build_csr(edge_index: torch.Tensor, num_nodes: int, transpose: bool = True, validate: bool = False) -> CSR:
+    """Device CSR of ``adj[ei[0],ei[1]]=1; adj+=eye`` (reference graph_attention.py:98-102)."""
+    lib = _lib.load()
+    if not edge_index.is_cuda:
+        raise RuntimeError("tagan_b200 has no CPU path: edge_index must live on a CUDA device")
+    ei = edge_index
+    if ei.dtype != torch.int64:
+        ei = ei.long()
+    ei = ei.contiguous()
+    e = ei.shape[1] if ei.numel() else 0
+    dev = ei.device
+    cap = e + num_nodes
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(num_nodes + 1, **i32)
+    col = torch.empty(max(cap, 1), **i32)
+    row = torch.empty(max(cap, 1), **i32)
+    status = torch.empty(1, **i32)
+    rowptr_t = row_t = perm_t = None
+    if transpose:
+        rowptr_t = torch.empty(num_nodes + 1, **i32)
+        row_t = torch.empty(max(cap, 1), **i32)
+        perm_t = torch.empty(max(cap, 1), **i32)
+    nbytes = lib.tagan_csr_workspace_bytes(e, num_nodes)
+    ws = workspace(nbytes, dev)
+    rc = lib.tagan_csr_build(_ptr(ei) if e else None, e, num_nodes, _ptr(rowptr), _ptr(col), _ptr(row),
+                             _ptr(rowptr_t), _ptr(row_t), _ptr(perm_t), _ptr(status), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "tagan_csr_build")
+    CALLS["n"] += 1
+    if validate and int(status.item()) != 0:
+        raise IndexError("edge_index out of range for num_nodes=%d" % num_nodes)
+    return CSR(num_nodes, e, rowptr, col, row, rowptr_t, row_t, perm_t, status)
+
+
+# ----------------------------------------------------------------------------------------
+# GEMM / Linear
+# ----------------------------------------------------------------------------------------
+def gemm(op: int, m: int, n: int, k: int, a, lda, b, ldb, bias, c, ldc, accumulate=False):
+    lib = _lib.load()
+    nbytes = lib.tagan_gemm_workspace_bytes(op, m, n, k)
+    ws = workspace(nbytes, c.device) if nbytes else None
+    rc = lib.tagan_gemm(op, m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(bias), _ptr(c), ldc, int(accumulate),
+                        GEMM_PRECISION, _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+    _lib.check(rc, "tagan_gemm")
+    CALLS["n"] += 1
+
+
+def colsum(x2d: torch.Tensor, rows: int, cols: int, ld: int) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    nbytes = lib.tagan_colsum_workspace_bytes(rows, cols)
+    ws = workspace(nbytes, x2d.device)
+    rc = lib.tagan_colsum(_ptr(x2d), ld, _ptr(out), _ptr(ws), ws.numel(), rows, cols, _stream())
+    _lib.check(rc, "tagan_colsum")
+    CALLS["n"] += 1
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b  (nn.Linear); dX = dY W, dW = dY^T X, db = colsum(dY)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2, m, k, ldx = _rows(x)
+        w = _f32c(weight)
+        n = w.shape[0]
+        y = torch.empty(m, n, dtype=torch.float32, device=x.device)
+        gemm(0, m, n, k, x2, ldx, w, w.stride(0), bias, y, n)
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = bias is not None
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], n)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2, m, n, ldy = _rows(dy)
+        k = w.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(m, k, dtype=torch.float32, device=dy.device)
+            gemm(1, m, k, n, dy2, ldy, w, w.stride(0), None, dx, k)
+            dx = dx.view(ctx.in_shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(n, k, dtype=torch.float32, device=dy.device)
+            ldx = x2.stride(0) if m > 1 else k
+            gemm(2, n, k, m, dy2, ldy, x2, ldx, None, dw, k)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2, m, n, ldy)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    return _LinearFn.apply(x, weight, bias)
+
+
+# ----------------------------------------------------------------------------------------
+# LayerNorm with fused residual / row scale
+# ----------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    """y = LN(x [+ res]) * rowscale; gamma=None means plain (x+res)*rowscale."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, rowscale):
+        lib = _lib.load()
+        x2, rows, cols, ldx = _rows(x)
+        r2 = ldres = None
+        if res is not None:
+            r2, _, _, ldres = _rows(res)
+        y = torch.empty(rows, cols, dtype=torch.float32, device=x.device)
+        xsum = torch.empty_like(y) if res is not None else None
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device) if gamma is not None else None
+        rstd = torch.empty_like(mean) if gamma is not None else None
+        rc = lib.tagan_layernorm_fwd(_ptr(x2), ldx, _ptr(r2), ldres or 0, _ptr(gamma), _ptr(beta), _ptr(rowscale),
+                                     _ptr(y), cols, _ptr(xsum), _ptr(mean), _ptr(rstd), rows, cols, _stream())
+        _lib.check(rc, "tagan_layernorm_fwd")
+        CALLS["n"] += 1
+        saved_x = xsum if xsum is not None else x2
+        ctx.save_for_backward(saved_x, gamma, rowscale, mean, rstd)
+        ctx.has_res = res is not None
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        xs, gamma, rowscale, mean, rstd = ctx.saved_tensors
+        dy2, rows, cols, lddy = _rows(dy)
+        dx = torch.empty(rows, cols, dtype=torch.float32, device=dy.device)
+        dgamma = dbeta = None
+        ws = None
+        if gamma is not None:
+            dgamma = torch.empty(cols, dtype=torch.float32, device=dy.device)
+            dbeta = torch.empty_like(dgamma)
+            ws = workspace(lib.tagan_layernorm_bwd_workspace_bytes(rows, cols), dy.device)
+        ldx = xs.stride(0) if rows > 1 else cols
+        rc = lib.tagan_layernorm_bwd(_ptr(dy2), lddy, _ptr(xs), ldx, _ptr(gamma), _ptr(rowscale), _ptr(mean),
+                                     _ptr(rstd), _ptr(dx), cols, 0, _ptr(dgamma), _ptr(dbeta), _ptr(ws),
+                                     ws.numel() if ws is not None else 0, rows, cols, _stream())
+        _lib.check(rc, "tagan_layernorm_bwd")
+        CALLS["n"] += 1
+        dx = dx.view(ctx.shape)
+        return dx, (dx if ctx.has_res else None), dgamma, dbeta, None
+
+
+def layer_norm(x, gamma=None, beta=None, res=None, rowscale=None):
+    """``LN(x + res)``; with gamma None just ``x + res`` (use_layer_norm=False paths)."""
+    if gamma is None and res is None and rowscale is None:
+        return x
+    return _LayerNormFn.apply(x, res, gamma, beta, rowscale)
+
+
+# ----------------------------------------------------------------------------------------
+# (a2-a4) geometric attention core
+# ----------------------------------------------------------------------------------------
+class _GeoAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, metric_param, csr: CSR, heads: int, metric: int, want_attn: bool):
+        lib = _lib.load()
+        qkv2, n, three_h, ld = _rows(qkv)
+        h = three_h // 3
+        ctxv = torch.empty(n, h, dtype=torch.float32, device=qkv.device)
+        lse = torch.empty(n, heads, dtype=torch.float32, device=qkv.device)
+        attn = None
+        if want_attn:
+            attn = torch.zeros(max(csr.num_edges + csr.num_nodes, 1), heads, dtype=torch.float32, device=qkv.device)
+        base = qkv2.data_ptr()
+        q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
+        rc = lib.tagan_geo_attn_fwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), n, h, heads, metric,
+                                    _ptr(metric_param), _ptr(ctxv), _ptr(lse), _ptr(attn), _stream())
+        _lib.check(rc, "tagan_geo_attn_fwd")
+        CALLS["n"] += 1
+        ctx.save_for_backward(qkv2, metric_param, ctxv, lse)
+        ctx.csr, ctx.heads, ctx.metric = csr, heads, metric
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+            return ctxv, attn
+        return ctxv, None
+
+    @staticmethod
+    def backward(ctx, dctx, _dattn):
+        lib = _lib.load()
+        qkv2, metric_param, ctxv, lse = ctx.saved_tensors
+        csr = ctx.csr
+        if csr.rowptr_t is None:
+            raise RuntimeError("CSR was built without its transpose; backward needs it")
+        n, three_h = qkv2.shape
+        h = three_h // 3
+        ld = qkv2.stride(0) if n > 1 else three_h
+        dctx = _f32c(dctx).contiguous()
+        dqkv = torch.empty(n, three_h, dtype=torch.float32, device=dctx.device)
+        delta = torch.empty(n, ctx.heads, dtype=torch.float32, device=dctx.device)
+        want_dp = metric_param is not None and ctx.metric in (7, 8)
+        dp_ws = torch.empty(n, ctx.heads, dtype=torch.float32, device=dctx.device) if want_dp else None
+        dparam = torch.empty(ctx.heads, dtype=torch.float32, device=dctx.device) if want_dp else None
+        base, dbase = qkv2.data_ptr(), dqkv.data_ptr()
+        q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
+        dq, dk, dv = (C.c_void_p(dbase + i * h * 4) for i in range(3))
+        rc = lib.tagan_geo_attn_bwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.rowptr_t), _ptr(csr.row_t),
+                                    n, h, ctx.heads, ctx.metric, _ptr(metric_param), _ptr(ctxv), _ptr(lse), _ptr(dctx),
+                                    dq, dk, dv, three_h, _ptr(delta), _ptr(dp_ws), _ptr(dparam), _stream())
+        _lib.check(rc, "tagan_geo_attn_bwd")
+        CALLS["n"] += 3 if want_dp else 2
+        return dqkv, dparam, None, None, None, None
+
+
+def geo_attention_core(qkv, csr: CSR, heads: int, metric: str, metric_param=None, want_attn=False):
+    """qkv ``[N,3H]`` (fused projection) -> ctx ``[N,H]`` (and per-entry weights ``[cap,h]``)."""
+    return _GeoAttnFn.apply(qkv, metric_param, csr, heads, METRIC_ID[metric], want_attn)
+
+
+# ----------------------------------------------------------------------------------------
+# element-wise helpers
+# ----------------------------------------------------------------------------------------
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _lib.load()
+        a2, b2 = _f32c(a).contiguous(), _f32c(b).contiguous()
+        out = torch.empty_like(a2)
+        rc = lib.tagan_axpby(_ptr(a2), 1.0, _ptr(b2), 1.0, _ptr(out), a2.numel(), _stream())
+        _lib.check(rc, "tagan_axpby")
+        CALLS["n"] += 1
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return d, d
+
+
+def add(a, b):
+    return _AddFn.apply(a, b)
+
+
+class _GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        x2 = _f32c(x).contiguous()
+        y = torch.empty_like(x2)
+        _lib.check(lib.tagan_gelu_fwd(_ptr(x2), _ptr(y), x2.numel(), _stream()), "tagan_gelu_fwd")
+        CALLS["n"] += 1
+        ctx.save_for_backward(x2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (x2,) = ctx.saved_tensors
+        dy2 = _f32c(dy).contiguous()
+        dx = torch.empty_like(x2)
+        _lib.check(lib.tagan_gelu_bwd(_ptr(dy2), _ptr(x2), _ptr(dx), x2.numel(), _stream()), "tagan_gelu_bwd")
+        CALLS["n"] += 1
+        return dx
+
+
+def gelu(x):
+    return _GeluFn.apply(x)
