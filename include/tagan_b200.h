@@ -140,6 +140,51 @@ int tagan_gemm(int32_t op /*0=NT,1=NN,2=TN*/, int64_t m, int64_t n, int64_t k,
                void* workspace, size_t workspace_bytes, tagan_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (b1,b2) per-node temporal attention over the snapshot axis.
+ * Replaces the score/bias/mask/softmax/`attn @ v` core of AsymmetricTemporalAttention.forward
+ * (src/tagan/layers/temporal_attention.py:1008-1183).  One CTA per node, (node,head) pairs on
+ * (sub-)warps, one lane per query row, K/V staged in shared memory, online softmax.
+ *   Q,K,V: rows of a fused [B*T,3H] projection (row stride ld).  Row of (node b, step t) is
+ *          b*T+t (time_major = 0, the [B,T,H] layout) or t*B+b (time_major = 1, the stacked
+ *          list-of-snapshots layout [T,B,H] -- avoids the permute of :972-976).
+ *   bias / bias_t: additive score bias [heads,T,T] in (i,j) and (j,i) order, shared by all nodes
+ *          (bias_bstride = 0) or per node (bias_bstride = heads*T*T); NULL = none.  It carries
+ *          relative_pos_table (:1011-1021), asymmetric_kernel (:1024-1027) and the RBF time bias
+ *          (:792-871); entries may be -inf (shared masks folded in).
+ *   ts [B,T] per-node timestamps (needed for mask bit1), band = 10.0 in the reference (:873-903)
+ *   mask_flags: bit0 causal (j<=i, :1073-1076); bit1 time band |ts_i-ts_j| <= band;
+ *          bit2 "mask is all ones => make it causal" (:1142-1148), decided on device from
+ *          *allones_flag (see tagan_tattn_mask_allones) -- no host sync.
+ *   mask: explicit uint8 keep-mask [mask_b, mask_h, T, T], mask_b in {1,B}, mask_h in {1,heads};
+ *          0 = masked, 1 = value was exactly 1.0, 2 = other non-zero.  NULL = none.
+ *   ctx: [rows,H] same row order as Q; lse [B,heads,T]; attn [B,heads,T,T] or NULL.
+ * ------------------------------------------------------------------------------------- */
+int tagan_tattn_fwd(const float* Q, const float* K, const float* V, int64_t ld,
+                    int64_t batch, int32_t T, int32_t hidden, int32_t heads, int32_t time_major,
+                    const float* bias_t, int64_t bias_bstride, const float* ts,
+                    int32_t mask_flags, float band, const int32_t* allones_flag,
+                    const uint8_t* mask, int32_t mask_b, int32_t mask_h,
+                    float* ctx, float* lse, float* attn, tagan_stream_t stream);
+/* Deterministic backward.  dQ,dK,dV rows like Q (row stride ldd).  dbias (nullable): gradient of
+ * the bias in (i,j) order -- [heads,T,T] reduced over nodes through `workspace` (per-CTA partial
+ * tables summed in a fixed order) when the bias is shared, [B,heads,T,T] when it is per node. */
+size_t tagan_tattn_bwd_workspace_bytes(int64_t batch, int32_t T, int32_t heads);
+int tagan_tattn_bwd(const float* Q, const float* K, const float* V, int64_t ld,
+                    int64_t batch, int32_t T, int32_t hidden, int32_t heads, int32_t time_major,
+                    const float* bias, const float* bias_t, int64_t bias_bstride, const float* ts,
+                    int32_t mask_flags, float band, const int32_t* allones_flag,
+                    const uint8_t* mask, int32_t mask_b, int32_t mask_h,
+                    const float* ctx, const float* lse, const float* dctx,
+                    float* dQ, float* dK, float* dV, int64_t ldd,
+                    float* dbias, void* workspace, size_t workspace_bytes, tagan_stream_t stream);
+/* allones_flag[0] = 1 iff every entry of the effective mask is exactly 1: all band tests
+ * |ts_i-ts_j| <= band pass (ts nullable) and every explicit mask byte == 1 (mask nullable).
+ * The data-dependent test of temporal_attention.py:1144, evaluated on device. */
+int tagan_tattn_mask_allones(const float* ts, int64_t batch, int32_t T, float band,
+                             const uint8_t* mask, int64_t mask_elems, int32_t* allones_flag,
+                             tagan_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Small fused element-wise helpers.
  * ------------------------------------------------------------------------------------- */
 /* out = alpha*a + beta*b (b may be NULL) */

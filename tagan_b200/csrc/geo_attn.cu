@@ -177,8 +177,8 @@ geo_attn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             float p1, p2;
             const float s = score_from_vectors<METRIC, VEC>(q[c], kk[u][c], group, par[c], qn[c], p1, p2);
             const float mn = fmaxf(m[c], s);
-            const float sc = __expf(m[c] - mn);
-            const float p = __expf(s - mn);
+            const float sc = expf(m[c] - mn);
+            const float p = expf(s - mn);
             l[c] = fmaf(l[c], sc, p);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[c][i] = fmaf(acc[c][i], sc, p * vv[u][c][i]);
@@ -208,7 +208,7 @@ geo_attn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
       for (int c = 0; c < NCHUNK; ++c) {
         float p1, p2;
         const float s = score_from_vectors<METRIC, VEC>(q[c], kr[c], group, par[c], qn[c], p1, p2);
-        if ((lane & (group - 1)) == 0) attn[(int64_t)e * heads + head[c]] = __expf(s - lse_c[c]);
+        if ((lane & (group - 1)) == 0) attn[(int64_t)e * heads + head[c]] = expf(s - lse_c[c]);
       }
     }
   }
@@ -279,7 +279,7 @@ geo_attn_bwd_row_kernel(const float* __restrict__ Q, const float* __restrict__ K
           for (int c = 0; c < NCHUNK; ++c) {
             float p1, p2;
             const float s = score_from_vectors<METRIC, VEC>(q[c], kk[u][c], group, par[c], qn[c], p1, p2);
-            const float a = __expf(s - ls[c]);
+            const float a = expf(s - ls[c]);
             float dp = 0.f;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) dp = fmaf(go[c][i], vv[u][c][i], dp);
@@ -357,7 +357,7 @@ geo_attn_bwd_col_kernel(const float* __restrict__ Q, const float* __restrict__ K
             }
             float p1, p2;
             const float s = score_from_vectors<METRIC, VEC>(qq[u][c], k[c], group, par[c], qn, p1, p2);
-            const float a = __expf(s - ls[u][c]);
+            const float a = expf(s - ls[u][c]);
             float dp = 0.f;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {

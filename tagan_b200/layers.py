@@ -119,3 +119,206 @@ class TAGANGraphAttention(nn.Module):
 
     def extra_repr(self) -> str:
         return f"hidden_dim={self.hidden_dim}"
+
+
+# ------------------------------------------------------------------------------------------
+# (b1,b2) temporal attention
+# ------------------------------------------------------------------------------------------
+class TimeEncoding(nn.Module):
+    """Parameter holder for the reference's ``TimeEncoding`` 'basis' branch
+    (src/tagan/layers/temporal_attention.py:112-116): ``basis_mu``, ``basis_sigma``, ``basis_proj``.
+    Only the 'basis' type is built by ``AsymmetricTemporalAttention`` (:696-701)."""
+
+    def __init__(self, d_model: int, num_bases: int = 16, encoding_type: str = "basis"):
+        super().__init__()
+        if encoding_type != "basis":
+            raise NotImplementedError("only time_encoding_type='basis' (the reference default) is supported")
+        self.d_model, self.num_bases, self.encoding_type = d_model, num_bases, encoding_type
+        self.basis_mu = nn.Parameter(torch.linspace(0, 1, num_bases))
+        self.basis_sigma = nn.Parameter(torch.ones(num_bases) * 0.1)
+        self.basis_proj = nn.Linear(num_bases, d_model)
+
+
+class AsymmetricTemporalAttention(nn.Module):
+    """Mirror of reference ``AsymmetricTemporalAttention``
+    (src/tagan/layers/temporal_attention.py:624-1217): same constructor, parameters and
+    ``forward(x, time_stamps=None, attention_mask=None, return_attention_weights=False)``.
+
+    The bias tables (relative position :1011-1021, asymmetric window :1024-1027, RBF time bias
+    :792-871) are folded into one additive ``[h,T,T]`` table with a handful of tiny torch ops (so
+    autograd carries their gradients); LayerNorm, projections and the per-node attention run in
+    libtagan_b200.  The reference's data-dependent mask rules are reproduced in ``_resolve_mask``.
+    """
+
+    MAX_PER_NODE_BIAS_ELEMS = 1 << 28
+
+    def __init__(self, hidden_dim: int, num_heads: int = 8, dropout: float = 0.1, causal: bool = False,
+                 time_aware: bool = True, use_layer_norm: bool = True, asymmetric_window_size: int = 5,
+                 future_discount: float = 0.8, relative_position_bias: bool = True,
+                 max_relative_position: int = 32, time_encoding_type: str = "basis", use_time_masks: bool = True):
+        super().__init__()
+        assert hidden_dim % num_heads == 0, "Hidden dimension must be divisible by number of heads"
+        self.hidden_dim, self.num_heads, self.dropout_prob = hidden_dim, num_heads, dropout
+        self.causal, self.use_layer_norm = causal, use_layer_norm
+        self.head_dim = hidden_dim // num_heads
+        self.time_aware = time_aware
+        self.asymmetric_window_size = asymmetric_window_size
+        self.future_discount = future_discount
+        self.relative_position_bias = relative_position_bias
+        self.max_relative_position = max_relative_position
+        self.time_encoding_type = time_encoding_type
+        self.use_time_masks = use_time_masks
+        self.q_linear = nn.Linear(hidden_dim, hidden_dim)
+        self.k_linear = nn.Linear(hidden_dim, hidden_dim)
+        self.v_linear = nn.Linear(hidden_dim, hidden_dim)
+        self.output_proj = nn.Linear(hidden_dim, hidden_dim)
+        if use_layer_norm:
+            self.layer_norm1 = nn.LayerNorm(hidden_dim)
+            self.layer_norm2 = nn.LayerNorm(hidden_dim)
+        self.attn_dropout = nn.Dropout(dropout)
+        self.output_dropout = nn.Dropout(dropout)
+        for lin in (self.q_linear, self.k_linear, self.v_linear, self.output_proj):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+        if relative_position_bias:
+            self.relative_pos_table = nn.Parameter(torch.zeros(2 * max_relative_position + 1, num_heads))
+            nn.init.xavier_uniform_(self.relative_pos_table)
+        if time_aware:
+            self.time_encoding = TimeEncoding(hidden_dim, num_bases=hidden_dim // 4, encoding_type=time_encoding_type)
+            self.time_q_proj = nn.Linear(hidden_dim, num_heads)
+            self.time_k_proj = nn.Linear(hidden_dim, num_heads)      # present but unused, as in the reference (:848)
+            nn.init.xavier_uniform_(self.time_q_proj.weight)
+            nn.init.xavier_uniform_(self.time_k_proj.weight)
+            nn.init.zeros_(self.time_q_proj.bias)
+            nn.init.zeros_(self.time_k_proj.bias)
+        self.asymmetric_kernel = nn.Parameter(torch.ones(2 * asymmetric_window_size + 1, num_heads))
+        with torch.no_grad():                                         # :717-730
+            w = asymmetric_window_size
+            for i in range(2 * w + 1):
+                dist = abs(i - w)
+                if i < w:
+                    self.asymmetric_kernel[i] = 1.0 - 0.5 * (dist / w)
+                elif i > w:
+                    self.asymmetric_kernel[i] = future_discount * (1.0 - 0.5 * (dist / w))
+                else:
+                    self.asymmetric_kernel[i] = 1.0
+
+    # -- additive bias tables -------------------------------------------------------------
+    def _position_bias(self, t: int, device) -> torch.Tensor:
+        pos = torch.arange(t, device=device)
+        rel = pos.unsqueeze(1) - pos.unsqueeze(0)                     # i - j
+        w = self.asymmetric_window_size
+        within = ((rel >= -w) & (rel <= w)).unsqueeze(-1).float()
+        bias = self.asymmetric_kernel[torch.clamp(rel + w, 0, 2 * w)] * within            # :756-790
+        if self.relative_position_bias:                               # :732-754
+            mr = self.max_relative_position
+            bias = bias + self.relative_pos_table[torch.clamp(rel + mr, 0, 2 * mr)]
+        return bias.permute(2, 0, 1)                                  # [h,T,T]
+
+    def _time_bias(self, ts: torch.Tensor) -> torch.Tensor:
+        """RBF time bias for timestamps ``ts`` [R,T] (R = 1 shared, R = B per node) -> [R,h,T,T].
+        ``TimeEncoding._get_basis_encoding`` (:122-220) folded with ``time_q_proj`` (:848)."""
+        te = self.time_encoding
+        diffs = ts.unsqueeze(2) - ts.unsqueeze(1)                     # :1033
+        tmin, tmax = diffs.min(), diffs.max()                         # global over the whole tensor (:142-143)
+        rng = tmax - tmin
+        ok = (tmax > tmin) & (rng > 1e-7)
+        tn = torch.where(ok, (diffs - tmin) / torch.where(ok, rng, torch.ones_like(rng)), torch.zeros_like(diffs))
+        sigma = torch.clamp(te.basis_sigma, min=1e-7)                 # :173-179 (no-op unless sigma < 1e-7)
+        expo = torch.clamp(-((tn.unsqueeze(-1) - te.basis_mu) ** 2 / (2 * sigma ** 2)), min=-88.0, max=88.0)
+        wc = self.time_q_proj.weight @ te.basis_proj.weight           # [h, nb]
+        bc = self.time_q_proj.weight @ te.basis_proj.bias + self.time_q_proj.bias
+        return (torch.exp(expo) @ wc.t() + bc).permute(0, 3, 1, 2)
+
+    # -- mask rules -----------------------------------------------------------------------
+    @staticmethod
+    def _encode_mask(m: torch.Tensor) -> torch.Tensor:
+        one = torch.ones((), dtype=torch.uint8, device=m.device)
+        return torch.where(m == 0, one * 0, torch.where(m == 1.0, one, one * 2))
+
+    def _resolve_mask(self, attention_mask, ts, b: int, t: int, device) -> ops.TemporalMask:
+        """Reproduce :1030-1172.  Returns the mask spec handed to the kernel."""
+        h = self.num_heads
+        flags = 1 if self.causal else 0                               # :1073-1076
+        am = attention_mask
+        band = self.time_aware and ts is not None and self.use_time_masks
+        combined = False
+        if band:                                                      # :1042-1069
+            if am is None:
+                am = "band"
+            elif not isinstance(am, list) and am.dim() >= 2 and tuple(am.shape[-2:]) == (t, t):
+                combined = True
+        if am is None:
+            return ops.TemporalMask(flags=flags)
+        if isinstance(am, str):                                       # time mask only
+            flag = ops.mask_allones_flag(ts, None, b, t, 10.0, device)
+            return ops.TemporalMask(flags=flags | 2 | 4, ts=ts, allones_flag=flag)
+        if isinstance(am, list):                                      # :1085-1108 -> ones -> causal either way
+            return ops.TemporalMask(flags=flags | 1)
+        am = am.to(device)
+        if am.dim() < 2 or am.shape[-1] != t or am.shape[-2] != t:    # :1118-1132 wrong shape => causal
+            return ops.TemporalMask(flags=flags | 1)
+        if combined:                                                  # attention_mask * time_mask -> [B,T,T]
+            if am.dim() > 3 or (am.dim() == 3 and am.shape[0] not in (1, b)):
+                raise NotImplementedError("attention_mask with >3 dims combined with time masks")
+            u8 = self._encode_mask(am).reshape(-1, 1, t, t).contiguous()
+            flag = ops.mask_allones_flag(ts, u8, b, t, 10.0, device)
+            return ops.TemporalMask(flags=flags | 2 | 4, ts=ts, mask=u8, allones_flag=flag)
+        expanded = am.unsqueeze(1)                                    # :1142
+        if expanded.numel() == 0:
+            return ops.TemporalMask(flags=flags)
+        if bool(torch.all(expanded == 1.0)):                          # :1144-1148 (host sync, as in the reference)
+            expanded = expanded * torch.tril(torch.ones(t, t, device=device))
+        try:                                                          # :1164-1170: failed broadcast => unmasked
+            if tuple(torch.broadcast_shapes(expanded.shape, (b, h, t, t))) != (b, h, t, t):
+                raise RuntimeError
+        except RuntimeError:
+            return ops.TemporalMask(flags=flags)
+        e4 = expanded.reshape((1,) * (4 - expanded.dim()) + tuple(expanded.shape))
+        u8 = self._encode_mask(e4).expand(e4.shape[0], e4.shape[1], t, t).contiguous()
+        return ops.TemporalMask(flags=flags, mask=u8)
+
+    # -- forward --------------------------------------------------------------------------
+    def forward(self, x, time_stamps: Optional[torch.Tensor] = None, attention_mask=None,
+                return_attention_weights: bool = False):
+        time_major = False
+        if isinstance(x, list):                                       # :928-976
+            cur = [t_[0] if isinstance(t_, list) and len(t_) > 0 else t_ for t_ in x]
+            mx = max(t_.shape[0] for t_ in cur)
+            cur = [F.pad(t_, (0, 0, 0, mx - t_.shape[0])) if t_.shape[0] < mx else t_ for t_ in cur]
+            phys = torch.stack(cur, dim=0)                            # [T,B,H]; logical x = phys.permute(1,0,2)
+            time_major = True
+            t, b, hdim = phys.shape
+        else:
+            phys = x.contiguous()
+            b, t, hdim = phys.shape
+        dev = phys.device
+        ln = self.use_layer_norm
+        rows = phys.reshape(-1, hdim)
+        xn = ops.layer_norm(rows, self.layer_norm1.weight, self.layer_norm1.bias) if ln else rows
+        w_qkv = torch.cat([self.q_linear.weight, self.k_linear.weight, self.v_linear.weight], 0)
+        b_qkv = torch.cat([self.q_linear.bias, self.k_linear.bias, self.v_linear.bias], 0)
+        qkv = ops.linear(xn, w_qkv, b_qkv)
+        bias = self._position_bias(t, dev)
+        ts = None
+        if self.time_aware and time_stamps is not None:
+            ts = time_stamps.to(dev).float()
+            shared = b == 1 or ts.stride(0) == 0 or bool((ts == ts[0:1]).all())
+            ts = ts.contiguous()
+            if shared:
+                bias = bias + self._time_bias(ts[0:1])[0]
+            else:
+                nb = self.time_encoding.num_bases
+                if b * t * t * max(nb, self.num_heads) > self.MAX_PER_NODE_BIAS_ELEMS:
+                    raise NotImplementedError("per-node timestamps at this size are not supported yet")
+                bias = bias.unsqueeze(0) + self._time_bias(ts)
+        tmask = self._resolve_mask(attention_mask, ts, b, t, dev)
+        ctx, attn = ops.temporal_attention_core(qkv, bias, tmask, b, t, self.num_heads, time_major,
+                                                want_attn=return_attention_weights)
+        o = ops.linear(ctx, self.output_proj.weight, self.output_proj.bias)
+        o = self.output_dropout(o)
+        out = ops.layer_norm(o, self.layer_norm2.weight, self.layer_norm2.bias, res=rows) if ln else ops.add(o, rows)
+        out = out.view(phys.shape)
+        if time_major:
+            out = out.permute(1, 0, 2)
+        return (out, attn) if return_attention_weights else out

@@ -349,3 +349,99 @@ class _GeluFn(torch.autograd.Function):
 
 def gelu(x):
     return _GeluFn.apply(x)
+
+
+# ----------------------------------------------------------------------------------------
+# (b1,b2) temporal attention core
+# ----------------------------------------------------------------------------------------
+@dataclass
+class TemporalMask:
+    """Resolved mask of one AsymmetricTemporalAttention call (see layers.py for the rules)."""
+    flags: int = 0                              # bit0 causal, bit1 band, bit2 allones => causal
+    band: float = 10.0
+    ts: Optional[torch.Tensor] = None           # [B,T] fp32
+    mask: Optional[torch.Tensor] = None         # uint8 [mask_b, mask_h, T, T]
+    allones_flag: Optional[torch.Tensor] = None  # int32 [1] device
+
+
+def mask_allones_flag(ts, mask_u8, batch: int, t: int, band: float, device) -> torch.Tensor:
+    lib = _lib.load()
+    flag = torch.empty(1, dtype=torch.int32, device=device)
+    rc = lib.tagan_tattn_mask_allones(_ptr(ts), batch, t, band, _ptr(mask_u8),
+                                      mask_u8.numel() if mask_u8 is not None else 0, _ptr(flag), _stream())
+    _lib.check(rc, "tagan_tattn_mask_allones")
+    CALLS["n"] += 2
+    return flag
+
+
+class _TAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, bias, tmask: TemporalMask, batch: int, t: int, heads: int, time_major: bool,
+                want_attn: bool):
+        lib = _lib.load()
+        qkv2, rows, three_h, ld = _rows(qkv)
+        h = three_h // 3
+        assert rows == batch * t
+        dev = qkv.device
+        ctxv = torch.empty(rows, h, dtype=torch.float32, device=dev)
+        lse = torch.empty(batch, heads, t, dtype=torch.float32, device=dev)
+        attn = torch.empty(batch, heads, t, t, dtype=torch.float32, device=dev) if want_attn else None
+        bias_c = bias_t = None
+        bstride = 0
+        if bias is not None:
+            bias_c = _f32c(bias).contiguous()
+            bias_t = bias_c.transpose(-1, -2).contiguous()
+            bstride = heads * t * t if bias_c.dim() == 4 else 0
+        m = tmask.mask
+        mb, mh = (m.shape[0], m.shape[1]) if m is not None else (1, 1)
+        base = qkv2.data_ptr()
+        q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
+        rc = lib.tagan_tattn_fwd(q, k, v, ld, batch, t, h, heads, int(time_major), _ptr(bias_t), bstride,
+                                 _ptr(tmask.ts), tmask.flags, tmask.band, _ptr(tmask.allones_flag), _ptr(m), mb, mh,
+                                 _ptr(ctxv), _ptr(lse), _ptr(attn), _stream())
+        _lib.check(rc, "tagan_tattn_fwd")
+        CALLS["n"] += 1
+        ctx.save_for_backward(qkv2, bias_c, bias_t, ctxv, lse)
+        ctx.tmask, ctx.dims, ctx.bstride = tmask, (batch, t, heads, time_major), bstride
+        ctx.bias_shape = bias.shape if bias is not None else None
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+        return ctxv, attn
+
+    @staticmethod
+    def backward(ctx, dctx, _dattn):
+        lib = _lib.load()
+        qkv2, bias_c, bias_t, ctxv, lse = ctx.saved_tensors
+        tmask = ctx.tmask
+        batch, t, heads, time_major = ctx.dims
+        rows, three_h = qkv2.shape
+        h = three_h // 3
+        ld = qkv2.stride(0) if rows > 1 else three_h
+        dev = dctx.device
+        dctx = _f32c(dctx).contiguous()
+        dqkv = torch.empty(rows, three_h, dtype=torch.float32, device=dev)
+        dbias = ws = None
+        if bias_c is not None and ctx.needs_input_grad[1]:
+            dbias = torch.empty_like(bias_c)
+            if ctx.bstride == 0:
+                ws = workspace(lib.tagan_tattn_bwd_workspace_bytes(batch, t, heads), dev)
+        m = tmask.mask
+        mb, mh = (m.shape[0], m.shape[1]) if m is not None else (1, 1)
+        base, dbase = qkv2.data_ptr(), dqkv.data_ptr()
+        q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
+        dq, dk, dv = (C.c_void_p(dbase + i * h * 4) for i in range(3))
+        rc = lib.tagan_tattn_bwd(q, k, v, ld, batch, t, h, heads, int(time_major), _ptr(bias_c), _ptr(bias_t),
+                                 ctx.bstride, _ptr(tmask.ts), tmask.flags, tmask.band, _ptr(tmask.allones_flag),
+                                 _ptr(m), mb, mh, _ptr(ctxv), _ptr(lse), _ptr(dctx), dq, dk, dv, three_h,
+                                 _ptr(dbias), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+        _lib.check(rc, "tagan_tattn_bwd")
+        CALLS["n"] += 2 if ws is not None else 1
+        if dbias is not None:
+            dbias = dbias.view(ctx.bias_shape)
+        return dqkv, dbias, None, None, None, None, None, None
+
+
+def temporal_attention_core(qkv, bias, tmask: TemporalMask, batch: int, t: int, heads: int,
+                            time_major: bool = False, want_attn: bool = False):
+    """qkv rows ``[B*T,3H]`` -> ctx rows ``[B*T,H]`` (+ ``attn[B,h,T,T]``)."""
+    return _TAttnFn.apply(qkv, bias, tmask, batch, t, heads, time_major, want_attn)

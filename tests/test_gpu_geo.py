@@ -148,7 +148,9 @@ def test_geo_attention_vs_reference_golden(dev, golden):
             if gref is None:
                 assert p.grad is None or float(p.grad.abs().max()) == 0.0
             else:
-                torch.testing.assert_close(p.grad.cpu(), gref, rtol=1e-4, atol=2e-5, msg=lambda m: f"{tag} d{k}: {m}")
+                # parameter gradients are sums over all nodes: atol scales with the gradient's magnitude
+                torch.testing.assert_close(p.grad.cpu(), gref, rtol=1e-4, atol=1e-5 * max(1.0, float(gref.abs().max())),
+                                           msg=lambda m: f"{tag} d{k}: {m}")
 
 
 @pytest.mark.parametrize("hidden,heads", [(32, 2), (64, 4), (128, 8), (128, 4), (256, 8), (512, 4)])
@@ -175,7 +177,9 @@ def test_geo_attention_vs_oracle_shapes(dev, hidden, heads, metric):
     torch.testing.assert_close(w["edge_attention"].detach().cpu(), aref.detach(), **TOL)
     torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=1e-4, atol=2e-5)
     for k, p in layer.geometric_attention.named_parameters():
-        torch.testing.assert_close(p.grad.cpu(), sd[k].grad, rtol=2e-4, atol=5e-5, msg=lambda m, k=k: f"d{k}: {m}")
+        gref = sd[k].grad
+        torch.testing.assert_close(p.grad.cpu(), gref, rtol=1e-4, atol=1e-5 * max(1.0, float(gref.abs().max())),
+                                   msg=lambda m, k=k: f"d{k}: {m}")
 
 
 def test_geo_attention_full_size_properties(dev):
