@@ -185,6 +185,36 @@ int tagan_tattn_mask_allones(const float* ts, int64_t batch, int32_t T, float ba
                              tagan_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (b3-b6) element-wise stages of temporal propagation; the Linears go through tagan_gemm and
+ * the LayerNorms (with the exp(-dt) decay as `rowscale`) through tagan_layernorm_*.
+ *   GRU cell  (TemporalGRUCell.forward, src/tagan/layers/temporal_propagation.py:531-539):
+ *       r,z = sigmoid(W[x^,h^]);  rh = r*h^;  h~ = tanh(Wc[x^,rh]);  hn = (1-z)*h^ + z*h~
+ *   Gating    (TemporalGatingUnit.forward :1043-1060):
+ *       u,r = sigmoid(W[c,p]);  rp = r*p;  cand = tanh(Wo[c,rp]);  out = (1-u)*c + u*cand (+c)
+ * `second` is the gated half of the concatenation (h^ / p), `base` the blended one (h^ / c).
+ * ------------------------------------------------------------------------------------- */
+/* g[rows,2H] = [reset | update] pre-activations -> r, z = sigmoid; rs[:, :] = r * second */
+int tagan_gates_fwd(const float* g, const float* second, int64_t lds, float* r, float* z,
+                    float* rs, int64_t ldrs, int64_t rows, int32_t H, tagan_stream_t stream);
+int tagan_gates_bwd(const float* drs, int64_t lddrs, const float* dz, const float* r, const float* z,
+                    const float* second, int64_t lds, float* dg, float* dsecond, int64_t ldds,
+                    int32_t accumulate, int64_t rows, int32_t H, tagan_stream_t stream);
+/* cand = tanh(cand_pre); out = (1-z)*base + z*cand (+ base if residual) */
+int tagan_blend_fwd(const float* cand_pre, const float* z, const float* base, int64_t ldb,
+                    float* cand, float* out, int32_t residual, int64_t rows, int32_t H,
+                    tagan_stream_t stream);
+int tagan_blend_bwd(const float* dout, const float* z, const float* cand, const float* base, int64_t ldb,
+                    float* dcand_pre, float* dz, float* dbase, int64_t lddb, int32_t accumulate,
+                    int32_t residual, int64_t rows, int32_t H, tagan_stream_t stream);
+/* sliding window over the snapshot axis of p[T, inner] (TemporalSkipConnection.forward :880-926):
+ * out[t] = agg_{u in [max(0,t-w), min(T,t+w+1))} p[u];  agg: 0 mean, 1 max, 2 sum. */
+int tagan_skip_window_fwd(const float* p, float* out, int32_t T, int64_t inner, int32_t window,
+                          int32_t agg, tagan_stream_t stream);
+int tagan_skip_window_bwd(const float* dg, const float* p, const float* agg_out, float* dp,
+                          int32_t T, int64_t inner, int32_t window, int32_t agg,
+                          tagan_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Small fused element-wise helpers.
  * ------------------------------------------------------------------------------------- */
 /* out = alpha*a + beta*b (b may be NULL) */

@@ -7,6 +7,9 @@ workloads (``synth``).  The package name is ``tagan_b200`` because the repositor
 """
 from . import _lib, ops  # noqa: F401
 from .layers import (AsymmetricTemporalAttention, GeometricAttention, TAGANGraphAttention,  # noqa: F401
-                     TimeEncoding)
+                     TemporalEvolutionLayer, TemporalGatingUnit, TemporalGRUCell, TemporalPropagation,
+                     TemporalSkipConnection, TimeEncoding)
 
-__all__ = ["ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding"]
+__all__ = ["ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
+           "TemporalGRUCell", "TemporalEvolutionLayer", "TemporalSkipConnection", "TemporalGatingUnit",
+           "TemporalPropagation"]

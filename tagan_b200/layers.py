@@ -322,3 +322,268 @@ class AsymmetricTemporalAttention(nn.Module):
         if time_major:
             out = out.permute(1, 0, 2)
         return (out, attn) if return_attention_weights else out
+
+
+# ------------------------------------------------------------------------------------------
+# (b3-b7) temporal propagation
+# ------------------------------------------------------------------------------------------
+def _ln_args(module, name, enabled):
+    if not enabled:
+        return None, None
+    ln = getattr(module, name)
+    return ln.weight, ln.bias
+
+
+class TemporalGRUCell(nn.Module):
+    """Mirror of reference ``TemporalGRUCell`` (src/tagan/layers/temporal_propagation.py:402-558)."""
+
+    def __init__(self, input_dim: int, hidden_dim: int, dropout: float = 0.1, use_layer_norm: bool = True):
+        super().__init__()
+        self.input_dim, self.hidden_dim, self.dropout, self.use_layer_norm = input_dim, hidden_dim, dropout, use_layer_norm
+        self.reset_gate = nn.Linear(input_dim + hidden_dim, hidden_dim)
+        self.update_gate = nn.Linear(input_dim + hidden_dim, hidden_dim)
+        self.candidate = nn.Linear(input_dim + hidden_dim, hidden_dim)
+        if use_layer_norm:
+            self.layer_norm_x = nn.LayerNorm(input_dim)
+            self.layer_norm_h = nn.LayerNorm(hidden_dim)
+            self.layer_norm_out = nn.LayerNorm(hidden_dim)
+        self.dropout_layer = nn.Dropout(dropout)
+        for lin in (self.reset_gate, self.update_gate, self.candidate):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+        nn.init.constant_(self.reset_gate.bias, 1.0)                  # :472-473
+        nn.init.constant_(self.update_gate.bias, 1.0)
+
+    def packed_gates(self):
+        return (torch.cat([self.reset_gate.weight, self.update_gate.weight], 0),
+                torch.cat([self.reset_gate.bias, self.update_gate.bias], 0))
+
+    def step(self, xhat, h, decay, w_rz, b_rz):
+        """xhat = LN_x(x) already applied; h = previous state or None; decay = exp(-dt) rows or None."""
+        if h is None:
+            hhat = torch.zeros(xhat.shape[0], self.hidden_dim, dtype=torch.float32, device=xhat.device)   # :503-504
+        else:
+            g, b = _ln_args(self, "layer_norm_h", self.use_layer_norm)
+            hhat = ops.layer_norm(h, g, b, rowscale=decay)            # :505-514
+        hn = ops.gru_like_cell(xhat, hhat, w_rz, b_rz, self.candidate.weight, self.candidate.bias,
+                               blend_with_first=False, residual=False)   # :531-539
+        hn = self.dropout_layer(hn)
+        g, b = _ln_args(self, "layer_norm_out", self.use_layer_norm)
+        return ops.layer_norm(hn, g, b)                               # :545-546
+
+    def forward(self, x, h=None, time_diff=None):
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        g, b = _ln_args(self, "layer_norm_x", self.use_layer_norm)
+        xhat = ops.layer_norm(x, g, b)
+        decay = None
+        if time_diff is not None and h is not None:
+            decay = torch.exp(-torch.clamp(time_diff.float(), min=0.0, max=10.0))
+        w_rz, b_rz = self.packed_gates()
+        return self.step(xhat, h, decay, w_rz, b_rz)
+
+
+class TemporalEvolutionLayer(nn.Module):
+    """Mirror of reference ``TemporalEvolutionLayer`` (temporal_propagation.py:561-765)."""
+
+    def __init__(self, input_dim: int, hidden_dim: int, dropout: float = 0.1, time_aware: bool = True,
+                 bidirectional: bool = False, use_layer_norm: bool = True, residual: bool = True):
+        super().__init__()
+        self.input_dim, self.hidden_dim, self.dropout = input_dim, hidden_dim, dropout
+        self.time_aware, self.bidirectional = time_aware, bidirectional
+        self.use_layer_norm, self.residual = use_layer_norm, residual
+        cell_dim = hidden_dim if not bidirectional else hidden_dim // 2
+        self.forward_cell = TemporalGRUCell(input_dim, cell_dim, dropout, use_layer_norm)
+        if bidirectional:
+            self.backward_cell = TemporalGRUCell(input_dim, hidden_dim // 2, dropout, use_layer_norm)
+        self.output_projection = nn.Linear(hidden_dim if bidirectional else cell_dim, hidden_dim)
+        if use_layer_norm:
+            self.layer_norm = nn.LayerNorm(hidden_dim)
+        self.dropout_layer = nn.Dropout(dropout)
+        nn.init.xavier_uniform_(self.output_projection.weight)
+        nn.init.zeros_(self.output_projection.bias)
+
+    def _scan(self, cell, xs3, ts, order, reverse):
+        t_steps = xs3.shape[0]
+        n = xs3.shape[1]
+        g, b = _ln_args(cell, "layer_norm_x", cell.use_layer_norm)
+        xhat = ops.layer_norm(xs3.reshape(t_steps * n, -1), g, b).view(t_steps, n, -1)   # LN_x for all steps at once
+        w_rz, b_rz = cell.packed_gates()
+        h = None
+        states = [None] * t_steps
+        for idx, t in enumerate(order):
+            decay = None
+            if ts is not None and self.time_aware and idx > 0:
+                decay = ops.decay_scale(ts, t + 1 if reverse else t)   # ts[:,t]-ts[:,t-1] / ts[:,t+1]-ts[:,t]
+            h = cell.step(xhat[t], h, decay, w_rz, b_rz)
+            states[t] = h
+        return states
+
+    def forward_stacked(self, xs3: torch.Tensor, time_stamps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """xs3 ``[T,N,in]`` -> ``[T,N,hidden]`` (:648-755)."""
+        t_steps, n, _ = xs3.shape
+        ts = time_stamps.float().contiguous() if time_stamps is not None else None
+        fwd = self._scan(self.forward_cell, xs3, ts, list(range(t_steps)), False)
+        if self.bidirectional:
+            bwd = self._scan(self.backward_cell, xs3, ts, list(range(t_steps - 1, -1, -1)), True)
+            s = torch.cat([torch.stack(fwd), torch.stack(bwd)], dim=-1)
+        else:
+            s = torch.stack(fwd)
+        o = ops.linear(s.view(t_steps * n, -1), self.output_projection.weight, self.output_projection.bias)
+        o = self.dropout_layer(o)
+        res = xs3.reshape(t_steps * n, -1) if (self.residual and self.input_dim == self.hidden_dim) else None
+        g, b = _ln_args(self, "layer_norm", self.use_layer_norm)
+        if g is None and res is not None:
+            o = ops.add(o, res)
+        else:
+            o = ops.layer_norm(o, g, b, res=res)
+        return o.view(t_steps, n, self.hidden_dim)
+
+    def forward(self, node_features_seq: List[torch.Tensor], time_stamps: Optional[torch.Tensor] = None):
+        out = self.forward_stacked(torch.stack(list(node_features_seq), 0), time_stamps)
+        return list(out.unbind(0))
+
+
+class TemporalSkipConnection(nn.Module):
+    """Mirror of reference ``TemporalSkipConnection`` (temporal_propagation.py:768-957)."""
+
+    def __init__(self, input_dim: int, hidden_dim: Optional[int] = None, window_size: int = 3,
+                 aggregation: str = "mean", dropout: float = 0.1, use_layer_norm: bool = True,
+                 apply_activation: bool = True, residual: bool = True):
+        super().__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim if hidden_dim is not None else input_dim
+        self.window_size, self.aggregation, self.dropout = window_size, aggregation, dropout
+        self.use_layer_norm, self.apply_activation, self.residual = use_layer_norm, apply_activation, residual
+        self.input_proj = nn.Linear(input_dim, self.hidden_dim)
+        self.output_proj = nn.Linear(self.hidden_dim, input_dim)
+        if use_layer_norm:
+            self.layer_norm1 = nn.LayerNorm(self.hidden_dim)
+            self.layer_norm2 = nn.LayerNorm(input_dim)
+        self.dropout_layer = nn.Dropout(dropout)
+        self.act_fn = nn.GELU()
+        for lin in (self.input_proj, self.output_proj):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+
+    def forward_stacked(self, e3: torch.Tensor) -> torch.Tensor:
+        """e3 ``[T,N,in]`` -> ``[T,N,in]`` (:846-946)."""
+        t_steps, n, _ = e3.shape
+        rows = e3.reshape(t_steps * n, -1)
+        p = ops.linear(rows, self.input_proj.weight, self.input_proj.bias)
+        if self.apply_activation:
+            p = ops.gelu(p)
+        g, b = _ln_args(self, "layer_norm1", self.use_layer_norm)
+        p = self.dropout_layer(ops.layer_norm(p, g, b))
+        agg = ops.skip_window(p.view(t_steps, n, self.hidden_dim), self.window_size, self.aggregation)
+        y = ops.linear(ops.gelu(agg).view(t_steps * n, -1), self.output_proj.weight, self.output_proj.bias)
+        y = self.dropout_layer(y)
+        g, b = _ln_args(self, "layer_norm2", self.use_layer_norm)
+        res = rows if self.residual else None
+        if g is None and res is not None:
+            y = ops.add(y, res)
+        else:
+            y = ops.layer_norm(y, g, b, res=res)
+        return y.view(t_steps, n, self.input_dim)
+
+    def forward(self, node_features_seq: List[torch.Tensor], time_weights=None):
+        return list(self.forward_stacked(torch.stack(list(node_features_seq), 0)).unbind(0))
+
+
+class TemporalGatingUnit(nn.Module):
+    """Mirror of reference ``TemporalGatingUnit`` (temporal_propagation.py:960-1075)."""
+
+    def __init__(self, input_dim: int, hidden_dim: Optional[int] = None, dropout: float = 0.1,
+                 use_layer_norm: bool = True, residual: bool = True):
+        super().__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim if hidden_dim is not None else input_dim
+        self.dropout, self.use_layer_norm, self.residual = dropout, use_layer_norm, residual
+        self.update_gate = nn.Linear(input_dim * 2, input_dim)
+        self.reset_gate = nn.Linear(input_dim * 2, input_dim)
+        self.output_gate = nn.Linear(input_dim * 2, input_dim)
+        if use_layer_norm:
+            self.layer_norm_in1 = nn.LayerNorm(input_dim)
+            self.layer_norm_in2 = nn.LayerNorm(input_dim)
+            self.layer_norm_out = nn.LayerNorm(input_dim)
+        self.dropout_layer = nn.Dropout(dropout)
+        for lin in (self.update_gate, self.reset_gate, self.output_gate):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+
+    def forward(self, current_feat: torch.Tensor, previous_feat: torch.Tensor) -> torch.Tensor:
+        g, b = _ln_args(self, "layer_norm_in1", self.use_layer_norm)
+        c = ops.layer_norm(current_feat, g, b)
+        g, b = _ln_args(self, "layer_norm_in2", self.use_layer_norm)
+        p = ops.layer_norm(previous_feat, g, b)
+        w_ru = torch.cat([self.reset_gate.weight, self.update_gate.weight], 0)
+        b_ru = torch.cat([self.reset_gate.bias, self.update_gate.bias], 0)
+        # the reference applies dropout between the blend and the residual add (:1052-1056); with
+        # dropout = 0 (the parity setting) the residual is fused into the blend kernel
+        fuse_res = self.residual and not (self.training and self.dropout > 0)
+        o = ops.gru_like_cell(c, p, w_ru, b_ru, self.output_gate.weight, self.output_gate.bias,
+                              blend_with_first=True, residual=fuse_res)
+        if self.residual and not fuse_res:
+            o = ops.add(self.dropout_layer(o), c)
+        g, b = _ln_args(self, "layer_norm_out", self.use_layer_norm)
+        return ops.layer_norm(o, g, b)
+
+
+class TemporalPropagation(nn.Module):
+    """Mirror of reference ``TemporalPropagation`` (temporal_propagation.py:1078-1522).
+
+    The reference's ``forward`` never completes: with node-id lists it raises
+    ``AttributeError`` at :1287 before any arithmetic, otherwise ``TypeError`` at :1505 after it;
+    ``TAGAN.forward`` catches that and falls back (model.py:302-309).  ``strict_reference=True``
+    (default) reproduces exactly that, so a patched reference model behaves identically.
+    ``forward_core`` is the runnable arithmetic (evolution -> skip -> LN(output_proj)), the part
+    the oracle restates and the benchmark times.
+    """
+
+    def __init__(self, input_dim: int, hidden_dim: int, dropout: float = 0.1, time_aware: bool = True,
+                 bidirectional: bool = False, use_layer_norm: bool = True, use_skip_connection: bool = True,
+                 use_gating: bool = True, window_size: int = 3, aggregation: str = "mean", residual: bool = True):
+        super().__init__()
+        self.input_dim, self.hidden_dim, self.dropout = input_dim, hidden_dim, dropout
+        self.time_aware, self.bidirectional, self.use_layer_norm = time_aware, bidirectional, use_layer_norm
+        self.use_skip_connection, self.use_gating = use_skip_connection, use_gating
+        self.window_size, self.aggregation, self.residual = window_size, aggregation, residual
+        self.evolution_layer = TemporalEvolutionLayer(input_dim, hidden_dim, dropout, time_aware, bidirectional,
+                                                      use_layer_norm, residual)
+        if use_skip_connection:
+            self.skip_connection = TemporalSkipConnection(hidden_dim, window_size=window_size, aggregation=aggregation,
+                                                          dropout=dropout, use_layer_norm=use_layer_norm,
+                                                          residual=residual)
+        if use_gating:
+            self.gating_unit = TemporalGatingUnit(hidden_dim, dropout=dropout, use_layer_norm=use_layer_norm,
+                                                  residual=residual)
+        self.state_tracking = nn.Parameter(torch.ones(1, 3), requires_grad=True)
+        self.dropout_layer = nn.Dropout(dropout)
+        self.output_proj = nn.Linear(hidden_dim, hidden_dim)
+        if use_layer_norm:
+            self.layer_norm = nn.LayerNorm(hidden_dim)
+        self.strict_reference = True
+
+    def forward_core(self, xs, time_stamps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """xs: list of ``[N,H]`` or stacked ``[T,N,H]`` -> ``[T,N,H]`` (:1343-1349, :1487-1500)."""
+        x3 = torch.stack(list(xs), 0) if isinstance(xs, (list, tuple)) else xs
+        e = self.evolution_layer.forward_stacked(x3, time_stamps)
+        if self.use_skip_connection:
+            e = self.skip_connection.forward_stacked(e)
+        t_steps, n, _ = e.shape
+        o = ops.linear(e.reshape(t_steps * n, -1), self.output_proj.weight, self.output_proj.bias)
+        o = self.dropout_layer(o)
+        g, b = _ln_args(self, "layer_norm", self.use_layer_norm)
+        return ops.layer_norm(o, g, b).view(t_steps, n, self.hidden_dim)
+
+    def forward(self, node_features_seq, node_masks_seq=None, time_stamps=None, memory_bank=None):
+        ids_given = (isinstance(node_masks_seq, list) and len(node_masks_seq) > 0
+                     and not isinstance(node_masks_seq[0], torch.Tensor))
+        if self.strict_reference:
+            if ids_given:
+                raise AttributeError("'TemporalPropagation' object has no attribute 'restrict_temporal_attention'")
+            raise TypeError("object of type 'NodeMemoryBank' has no len()")
+        if isinstance(node_features_seq, torch.Tensor):
+            node_features_seq = [node_features_seq]
+        out = self.forward_core(node_features_seq, time_stamps)
+        return list(out.unbind(0)), memory_bank

@@ -445,3 +445,134 @@ def temporal_attention_core(qkv, bias, tmask: TemporalMask, batch: int, t: int, 
                             time_major: bool = False, want_attn: bool = False):
     """qkv rows ``[B*T,3H]`` -> ctx rows ``[B*T,H]`` (+ ``attn[B,h,T,T]``)."""
     return _TAttnFn.apply(qkv, bias, tmask, batch, t, heads, time_major, want_attn)
+
+
+# ----------------------------------------------------------------------------------------
+# (b3-b6) propagation element-wise stages
+# ----------------------------------------------------------------------------------------
+class _GatesFn(torch.autograd.Function):
+    """g [rows,2H] = [reset|update] pre-activations, second [rows,H] -> (r*second, z)."""
+
+    @staticmethod
+    def forward(ctx, g, second):
+        lib = _lib.load()
+        g2, rows, two_h, _ = _rows(g)
+        g2 = g2.contiguous()
+        h = two_h // 2
+        s2, _, _, lds = _rows(second)
+        r = torch.empty(rows, h, dtype=torch.float32, device=g.device)
+        z = torch.empty_like(r)
+        rs = torch.empty_like(r)
+        _lib.check(lib.tagan_gates_fwd(_ptr(g2), _ptr(s2), lds, _ptr(r), _ptr(z), _ptr(rs), h, rows, h, _stream()),
+                   "tagan_gates_fwd")
+        CALLS["n"] += 1
+        ctx.save_for_backward(r, z, s2)
+        return rs, z
+
+    @staticmethod
+    def backward(ctx, drs, dz):
+        lib = _lib.load()
+        r, z, s2 = ctx.saved_tensors
+        rows, h = r.shape
+        lds = s2.stride(0) if rows > 1 else h
+        drs = _f32c(drs).contiguous()
+        dz = _f32c(dz).contiguous()
+        dg = torch.empty(rows, 2 * h, dtype=torch.float32, device=r.device)
+        dsecond = torch.empty(rows, h, dtype=torch.float32, device=r.device)
+        _lib.check(lib.tagan_gates_bwd(_ptr(drs), h, _ptr(dz), _ptr(r), _ptr(z), _ptr(s2), lds, _ptr(dg),
+                                       _ptr(dsecond), h, 0, rows, h, _stream()), "tagan_gates_bwd")
+        CALLS["n"] += 1
+        return dg, dsecond
+
+
+class _BlendFn(torch.autograd.Function):
+    """out = (1-z)*base + z*tanh(cand_pre) (+ base)."""
+
+    @staticmethod
+    def forward(ctx, cand_pre, z, base, residual: bool):
+        lib = _lib.load()
+        c2, rows, h, _ = _rows(cand_pre)
+        c2 = c2.contiguous()
+        z2 = _f32c(z).contiguous()
+        b2, _, _, ldb = _rows(base)
+        cand = torch.empty(rows, h, dtype=torch.float32, device=c2.device)
+        out = torch.empty_like(cand)
+        _lib.check(lib.tagan_blend_fwd(_ptr(c2), _ptr(z2), _ptr(b2), ldb, _ptr(cand), _ptr(out), int(residual), rows, h,
+                                       _stream()), "tagan_blend_fwd")
+        CALLS["n"] += 1
+        ctx.save_for_backward(z2, cand, b2)
+        ctx.residual = residual
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        z2, cand, b2 = ctx.saved_tensors
+        rows, h = cand.shape
+        ldb = b2.stride(0) if rows > 1 else h
+        dout = _f32c(dout).contiguous()
+        dc = torch.empty_like(cand)
+        dz = torch.empty_like(cand)
+        db = torch.empty_like(cand)
+        _lib.check(lib.tagan_blend_bwd(_ptr(dout), _ptr(z2), _ptr(cand), _ptr(b2), ldb, _ptr(dc), _ptr(dz), _ptr(db), h,
+                                       0, int(ctx.residual), rows, h, _stream()), "tagan_blend_bwd")
+        CALLS["n"] += 1
+        return dc, dz, db, None
+
+
+def gru_like_cell(first, second, w_rz, b_rz, w_c, b_c, blend_with_first: bool, residual: bool):
+    """Shared body of TemporalGRUCell (:531-539) and TemporalGatingUnit (:1043-1060).
+
+    first/second: the two normalised halves of the concatenation; w_rz = [W_reset; W_update]."""
+    g = linear(torch.cat([first, second], dim=-1), w_rz, b_rz)
+    rs, z = _GatesFn.apply(g, second)
+    cand_pre = linear(torch.cat([first, rs], dim=-1), w_c, b_c)
+    return _BlendFn.apply(cand_pre, z, first if blend_with_first else second, residual)
+
+
+class _WindowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, window: int, agg: int):
+        lib = _lib.load()
+        p2 = _f32c(p).contiguous()
+        t = p2.shape[0]
+        inner = p2.numel() // max(t, 1)
+        out = torch.empty_like(p2)
+        _lib.check(lib.tagan_skip_window_fwd(_ptr(p2), _ptr(out), t, inner, window, agg, _stream()),
+                   "tagan_skip_window_fwd")
+        CALLS["n"] += 1
+        ctx.save_for_backward(*( (p2, out) if agg == 1 else () ))
+        ctx.cfg = (t, inner, window, agg)
+        return out
+
+    @staticmethod
+    def backward(ctx, dg):
+        lib = _lib.load()
+        t, inner, window, agg = ctx.cfg
+        p2 = out = None
+        if agg == 1:
+            p2, out = ctx.saved_tensors
+        dg = _f32c(dg).contiguous()
+        dp = torch.empty_like(dg)
+        _lib.check(lib.tagan_skip_window_bwd(_ptr(dg), _ptr(p2), _ptr(out), _ptr(dp), t, inner, window, agg, _stream()),
+                   "tagan_skip_window_bwd")
+        CALLS["n"] += 1
+        return dp, None, None
+
+
+AGG_ID = {"mean": 0, "max": 1, "sum": 2}
+
+
+def skip_window(p, window: int, aggregation: str):
+    """p ``[T, ...]`` -> sliding-window aggregate over the leading (snapshot) axis."""
+    return _WindowFn.apply(p, window, AGG_ID.get(aggregation, 2))
+
+
+def decay_scale(ts: torch.Tensor, t: int) -> torch.Tensor:
+    """exp(-clamp(ts[:,t]-ts[:,t-1], 0, 10)) per row (TemporalGRUCell :509-514)."""
+    lib = _lib.load()
+    ts2 = _f32c(ts)
+    out = torch.empty(ts2.shape[0], dtype=torch.float32, device=ts2.device)
+    _lib.check(lib.tagan_decay_scale(_ptr(ts2), ts2.stride(0), t, _ptr(out), ts2.shape[0], _stream()), "tagan_decay_scale")
+    CALLS["n"] += 1
+    return out

@@ -48,4 +48,5 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src or f == "__init__.py" and "import oracle" not in src, f
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "ref_loader" not in src and "/root/reference" not in src, f

@@ -11,6 +11,16 @@ from oracle import restate as R
 
 pytestmark = pytest.mark.gpu
 TOL = dict(rtol=1e-4, atol=1e-5)
+# Gradients that are analytically ZERO by softmax shift-invariance (a key bias shifts every score of
+# a row equally): both sides hold only rounding noise, compared with atol 1e-4.
+ZERO_GRADS = {"k_linear.bias"}
+
+
+def _gtol(name, gref, metric="scaled_dot_product"):
+    """Parameter gradients are sums over all nodes/entries: atol scales with the gradient magnitude."""
+    if name in ZERO_GRADS and metric in ("scaled_dot_product", "dot_product"):
+        return dict(rtol=1e-4, atol=1e-4)
+    return dict(rtol=1e-4, atol=1e-5 * max(1.0, float(gref.abs().max())))
 
 
 @pytest.fixture(scope="module")
@@ -148,8 +158,7 @@ def test_geo_attention_vs_reference_golden(dev, golden):
             if gref is None:
                 assert p.grad is None or float(p.grad.abs().max()) == 0.0
             else:
-                # parameter gradients are sums over all nodes: atol scales with the gradient's magnitude
-                torch.testing.assert_close(p.grad.cpu(), gref, rtol=1e-4, atol=1e-5 * max(1.0, float(gref.abs().max())),
+                torch.testing.assert_close(p.grad.cpu(), gref, **_gtol(k, gref, c["metric"]),
                                            msg=lambda m: f"{tag} d{k}: {m}")
 
 
@@ -175,11 +184,16 @@ def test_geo_attention_vs_oracle_shapes(dev, hidden, heads, metric):
     (out * wout.to(dev)).sum().backward()
     torch.testing.assert_close(out.detach().cpu(), ref.detach(), **TOL)
     torch.testing.assert_close(w["edge_attention"].detach().cpu(), aref.detach(), **TOL)
-    torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=1e-4, atol=2e-5)
+    # manhattan's |q-k| is not differentiable at 0: a sign flip from a 1-ulp difference in q-k moves a
+    # handful of gradient entries, so its gradients are compared with atol 1e-4
+    gat = 1e-4 if metric == "manhattan" else 2e-5
+    torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=1e-4, atol=gat)
     for k, p in layer.geometric_attention.named_parameters():
         gref = sd[k].grad
-        torch.testing.assert_close(p.grad.cpu(), gref, rtol=1e-4, atol=1e-5 * max(1.0, float(gref.abs().max())),
-                                   msg=lambda m, k=k: f"d{k}: {m}")
+        tol = _gtol(k, gref, metric)
+        if metric == "manhattan":
+            tol["atol"] = max(tol["atol"], 1e-4)
+        torch.testing.assert_close(p.grad.cpu(), gref, **tol, msg=lambda m, k=k: f"d{k}: {m}")
 
 
 def test_geo_attention_full_size_properties(dev):

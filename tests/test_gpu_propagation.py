@@ -1,0 +1,126 @@
+"""GPU parity tests for hot-path rows b3-b7 (GRU cell, evolution layer, skip connection, gating
+unit, propagation core) through the C ABI against the reference golden vectors and the oracle.
+fp32, rtol 1e-4 / atol 1e-5 (parameter gradients: atol scaled by gradient magnitude)."""
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=1e-4, atol=1e-5)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _gtol(gref):
+    return dict(rtol=1e-4, atol=1e-5 * max(1.0, float(gref.abs().max())))
+
+
+def _check_param_grads(module, grads, tag):
+    params = dict(module.named_parameters())
+    for k, gref in grads.items():
+        g = params[k].grad
+        if gref is None:
+            assert g is None or float(g.abs().max()) == 0.0, (tag, k)
+        else:
+            assert g is not None, (tag, k)
+            torch.testing.assert_close(g.cpu(), gref, **_gtol(gref), msg=lambda m, k=k: f"{tag} d{k}: {m}")
+
+
+def test_gru_cell_golden(dev, golden):
+    import tagan_b200
+    c = golden("propagation.pt")["gru_cell"]
+    cell = tagan_b200.TemporalGRUCell(16, 16, dropout=0.0).to(dev)
+    cell.load_state_dict(c["sd"])
+    x = c["x"].to(dev).requires_grad_(True)
+    h = c["h"].to(dev).requires_grad_(True)
+    torch.testing.assert_close(cell(x, None, None).detach().cpu(), c["out_h_none"], **TOL)
+    o = cell(x, h, c["td"].to(dev))
+    torch.testing.assert_close(o.detach().cpu(), c["out"], **TOL)
+    (o * c["wout"].to(dev)).sum().backward()
+    torch.testing.assert_close(x.grad.cpu(), c["dx"], **TOL)
+    torch.testing.assert_close(h.grad.cpu(), c["dh"], **TOL)
+    _check_param_grads(cell, c["grads"], "gru_cell")
+
+
+def _seq_case(dev, c, module, call, tag):
+    module.load_state_dict(c["sd"])
+    xs = [t.to(dev).requires_grad_(True) for t in c["xs"]]
+    ys = call(module, xs)
+    for y, yr in zip(ys, c["outs"]):
+        torch.testing.assert_close(y.detach().cpu(), yr, **TOL, msg=lambda m: f"{tag} out: {m}")
+    sum((y * w.to(dev)).sum() for y, w in zip(ys, c["wout"])).backward()
+    for a, b in zip(xs, c["dxs"]):
+        torch.testing.assert_close(a.grad.cpu(), b, **TOL, msg=lambda m: f"{tag} dx: {m}")
+    _check_param_grads(module, c["grads"], tag)
+
+
+def test_evolution_skip_propagation_golden(dev, golden):
+    import tagan_b200
+    g = golden("propagation.pt")
+    ts = g["evolution"]["ts"].to(dev)
+    _seq_case(dev, g["evolution"], tagan_b200.TemporalEvolutionLayer(16, 16, dropout=0.0).to(dev),
+              lambda m, xs: m(xs, ts), "evolution")
+    _seq_case(dev, g["evolution_no_ts"], tagan_b200.TemporalEvolutionLayer(16, 16, dropout=0.0).to(dev),
+              lambda m, xs: m(xs, None), "evolution_no_ts")
+    for agg in ("mean", "max", "sum"):
+        c = g["skip_" + agg]
+        _seq_case(dev, c, tagan_b200.TemporalSkipConnection(16, window_size=c["window"], aggregation=agg,
+                                                            dropout=0.0).to(dev), lambda m, xs: m(xs), "skip_" + agg)
+    tp = tagan_b200.TemporalPropagation(16, 16, dropout=0.0).to(dev)
+    _seq_case(dev, g["propagation_core"], tp, lambda m, xs: list(m.forward_core(xs, ts).unbind(0)), "propagation_core")
+
+
+def test_gating_unit_golden(dev, golden):
+    import tagan_b200
+    c = golden("propagation.pt")["gating"]
+    gu = tagan_b200.TemporalGatingUnit(16, dropout=0.0).to(dev)
+    gu.load_state_dict(c["sd"])
+    cur = c["cur"].to(dev).requires_grad_(True)
+    prev = c["prev"].to(dev).requires_grad_(True)
+    o = gu(cur, prev)
+    torch.testing.assert_close(o.detach().cpu(), c["out"], **TOL)
+    (o * c["wout"].to(dev)).sum().backward()
+    torch.testing.assert_close(cur.grad.cpu(), c["dcur"], **TOL)
+    torch.testing.assert_close(prev.grad.cpu(), c["dprev"], **TOL)
+    _check_param_grads(gu, c["grads"], "gating")
+
+
+def test_propagation_strict_reference_raises(dev):
+    """The reference's forward never completes; the drop-in reproduces the exceptions
+    so TAGAN.forward takes the same fallback."""
+    import tagan_b200
+    tp = tagan_b200.TemporalPropagation(16, 16, dropout=0.0).to(dev)
+    xs = [torch.randn(4, 16, device=dev) for _ in range(3)]
+    with pytest.raises(AttributeError):
+        tp(xs, [[0, 1, 2, 3]] * 3, time_stamps=None, memory_bank=None)
+    with pytest.raises(TypeError):
+        tp(xs)
+
+
+@pytest.mark.parametrize("n,t,hidden", [(1000, 16, 128), (300, 32, 64), (64, 8, 256)])
+def test_propagation_core_vs_oracle(dev, n, t, hidden):
+    import tagan_b200
+    torch.manual_seed(n)
+    tp = tagan_b200.TemporalPropagation(hidden, hidden, dropout=0.0).to(dev)
+    xs = [torch.randn(n, hidden) for _ in range(t)]
+    ts = torch.cumsum(torch.rand(n, t) * 2.0, 1)
+    wout = torch.randn(t, n, hidden)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in tp.state_dict().items()}
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    ref = torch.stack(R.propagation_core(xr, ts, sd), 0)
+    (ref * wout).sum().backward()
+    xd = [x.to(dev).requires_grad_(True) for x in xs]
+    out = tp.forward_core(xd, ts.to(dev))
+    (out * wout.to(dev)).sum().backward()
+    torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-4, atol=2e-5)
+    for a, b in zip(xd, xr):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-4, atol=2e-5)
+    for k, p in tp.named_parameters():
+        gref = sd[k].grad
+        if gref is None:
+            continue
+        torch.testing.assert_close(p.grad.cpu(), gref, **_gtol(gref), msg=lambda m, k=k: f"d{k}: {m}")
