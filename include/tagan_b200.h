@@ -215,6 +215,37 @@ int tagan_skip_window_bwd(const float* dg, const float* p, const float* agg_out,
                           tagan_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (c1-c3) node memory bank on dense device tables keyed by slot (= node id).
+ * Replaces NodeMemoryBank's python dicts (src/tagan/utils/memory_bank.py:14-360).
+ *   table[cap,H] fp32 states; valid,has_seen u8[cap]; last_seen,inactivity,frequency i32[cap].
+ *   status[1] int32 is set to 1 if an id was outside [0, cap).
+ * ------------------------------------------------------------------------------------- */
+/* get_states (:187-211): out[i] = table[ids[i]] or zeros; unknown ids are inserted with a zero
+ * state, inactivity 0 and no last_seen. */
+int tagan_bank_gather(float* table, uint8_t* valid, int32_t* inactivity, const int32_t* ids,
+                      float* out, int64_t M, int32_t H, int32_t capacity, int32_t* status,
+                      tagan_stream_t stream);
+/* update (:65-173): inactivity++ on every known id; frequency++ per occurrence; the LAST occurrence
+ * of a listed id writes its state -- blended with the stored one (w*prev + (1-w)*cur, :121-129)
+ * only if the id is listed once and reappears after a gap (last_seen < timestep-1); every stored id
+ * NOT listed is multiplied by decay^inactivity (:149-153); ids with inactivity > max_inactivity
+ * are pruned (:156-166); size_out[0] = surviving ids (:169).  Only min(num_ids, num_states) ids
+ * have a state row (bounds check :95); the rest still count as listed.
+ *   w23 (HOST): {w(gap 2), 1-w(gap 2), w(gap>=3), 1-w(gap>=3)} rounded to fp32 from the python
+ *   doubles max(0.4, decay**min(gap,3)); decay_pow (DEVICE) [decay_pow_len]: decay**k rounded from
+ *   double, `decay` (double) used beyond the table.  mark_ws: int32[2*capacity] scratch.
+ * States and all integer bookkeeping are bit-exact with the reference. */
+int tagan_bank_update(float* table, uint8_t* valid, uint8_t* has_seen, int32_t* last_seen,
+                      int32_t* inactivity, int32_t* frequency, const int32_t* ids, int64_t num_ids,
+                      const float* states, int64_t lds, int64_t num_states, int32_t H,
+                      int32_t capacity, int32_t timestep, const float* w23, const float* decay_pow,
+                      int32_t decay_pow_len, double decay, int32_t max_inactivity, int32_t* mark_ws,
+                      int32_t* size_out, int32_t* status, tagan_stream_t stream);
+/* decay_all (:222-225): every stored state *= decay */
+int tagan_bank_decay_all(float* table, const uint8_t* valid, float decay, int32_t H, int32_t capacity,
+                         tagan_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Small fused element-wise helpers.
  * ------------------------------------------------------------------------------------- */
 /* out = alpha*a + beta*b (b may be NULL) */

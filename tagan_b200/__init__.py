@@ -10,6 +10,8 @@ from .layers import (AsymmetricTemporalAttention, GeometricAttention, TAGANGraph
                      TemporalEvolutionLayer, TemporalGatingUnit, TemporalGRUCell, TemporalPropagation,
                      TemporalSkipConnection, TimeEncoding)
 
-__all__ = ["ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
+from .memory_bank import NodeMemoryBank  # noqa: F401,E402
+
+__all__ = ["NodeMemoryBank", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
            "TemporalGRUCell", "TemporalEvolutionLayer", "TemporalSkipConnection", "TemporalGatingUnit",
            "TemporalPropagation"]

@@ -50,6 +50,10 @@ SIGNATURES = {
     "tagan_blend_bwd": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i64, _i32, _p]),
     "tagan_skip_window_fwd": (_i32, [_p, _p, _i32, _i64, _i32, _i32, _p]),
     "tagan_skip_window_bwd": (_i32, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _p]),
+    "tagan_bank_gather": (_i32, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p]),
+    "tagan_bank_update": (_i32, [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i32,
+                                 C.c_double, _i32, _p, _p, _p, _p]),
+    "tagan_bank_decay_all": (_i32, [_p, _p, _f32, _i32, _i32, _p]),
     "tagan_axpby": (_i32, [_p, _f32, _p, _f32, _p, _i64, _p]),
     "tagan_gelu_fwd": (_i32, [_p, _p, _i64, _p]),
     "tagan_gelu_bwd": (_i32, [_p, _p, _p, _i64, _p]),
