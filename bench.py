@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the TAGAN hot path: edge-snapshots/s of one "TAGAN layer" forward+backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A step = geometric attention layer over all T snapshots (device CSR build included) + propagation
+core + temporal attention + memory-bank gather/update per snapshot, forward and backward, fp32,
+dropout 0, on synthetic temporal graphs of the named config.  Multi-GPU is
+data-parallel: one graph sequence per GPU, replicated weights, one NCCL all-reduce of the gradients
+per step (weak scaling).  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the CPU oracle port of the same path (oracle/restate.py, pinned against the
+unmodified reference by tests/golden) on all host cores, on a bounded sample of the same workload:
+the reference's own dense N x N implementation cannot allocate this config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "edge-snapshots/sec TAGAN layer fwd+bwd"
+UNIT = "edge-snapshots/s"
+CPU_SAMPLE_SNAPSHOTS = 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--metric", default="euclidean", help="DistanceMetric of the geometric layer (reference default)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bank", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------
+def cpu_sample_step_factory(w, metric, seed=0):
+    """Bounded sample of the workload for the CPU port: same N, E, H, heads; T = 2 snapshots."""
+    import contextlib
+    import io
+    from oracle import restate as R
+    from tagan_b200 import synth
+    import tagan_b200
+    torch.set_num_threads(os.cpu_count() or 1)
+    xs, eis, ts = synth.make_sequence(w, seed=seed, snapshots=CPU_SAMPLE_SNAPSHOTS)
+    torch.manual_seed(0)
+    layer = tagan_b200.TAGANLayer(w.hidden, w.heads, metric)
+    sdg = {k: v.detach().clone().requires_grad_(True) for k, v in layer.geometric.geometric_attention.state_dict().items()}
+    sdp = {k: v.detach().clone().requires_grad_(True) for k, v in layer.propagation.state_dict().items()}
+    sdt = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in layer.temporal_attention.state_dict().items()}
+
+    def step():
+        with contextlib.redirect_stdout(io.StringIO()):
+            xr = [x.clone().requires_grad_(True) for x in xs]
+            csrs = [R.build_csr(e, w.num_nodes) for e in eis]
+            out = R.tagan_layer(xr, eis, ts, sdg, sdp, sdt, w.heads, metric, csrs=csrs)
+            out.square().mean().backward()
+    units = w.num_edges * CPU_SAMPLE_SNAPSHOTS
+    desc = (f"{w.name}: same N={w.num_nodes}, E={w.num_edges}/snapshot, H={w.hidden}, h={w.heads}, "
+            f"T={CPU_SAMPLE_SNAPSHOTS} of {w.snapshots} snapshots; CSR build + layer fwd+bwd, oracle/restate.py (sparse "
+            f"torch CPU port of the reference semantics)")
+    return step, units, desc
+
+
+def run_reference(args):
+    from tagan_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = synth.WORKLOADS[args.workload]
+    step, units, desc = cpu_sample_step_factory(w, args.metric)
+    for _ in range(min(args.warmup, 1)):          # CPU path: one warm-up is enough to fault pages in
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = units * args.steps / dt
+    cores = torch.get_num_threads()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": w.name, "distance_metric": args.metric, "sample": desc},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU leg
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import tagan_b200
+    from tagan_b200 import ops, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the TAGAN hot path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = synth.WORKLOADS[args.workload]
+    t_steps, n, e, hdim = w.snapshots, w.num_nodes, w.num_edges, w.hidden
+
+    # synthetic inputs: pinned host copies (e2e arm) and resident device copies (kernel arm)
+    xs_h, eis_h, ts_h = synth.make_sequence(w, seed=rank, pin=True)
+    xs_d = [x.to(dev, non_blocking=True) for x in xs_h]
+    eis_d = [ei.to(dev, non_blocking=True) for ei in eis_h]
+    ts_d = torch.arange(t_steps, dtype=torch.float32, device=dev).expand(n, t_steps)   # shared timestamps (stride 0)
+    ids = torch.arange(n, dtype=torch.int32, device=dev)
+    torch.manual_seed(0)
+    layer = tagan_b200.TAGANLayer(hdim, w.heads, args.metric).to(dev)
+    bank = None
+    if not args.no_bank:
+        bank = tagan_b200.NodeMemoryBank(hdim, 0.8, 3, device=dev, capacity=n)
+        bank.check_range = False
+    params = [p for p in layer.parameters() if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev) if world > 1 else None
+
+    def step(xs, eis):
+        layer.zero_grad(set_to_none=True)
+        out = layer(xs, eis, ts_d, bank=bank, node_ids=[ids] * t_steps)
+        loss = out.square().mean()
+        loss.backward()
+        if world > 1:                       # data-parallel: one flat NCCL all-reduce of the gradients
+            off = 0
+            for p in params:
+                g = p.grad if p.grad is not None else torch.zeros_like(p)
+                flat[off:off + p.numel()].copy_(g.reshape(-1))
+                off += p.numel()
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(xs_d, eis_d)
+    barrier()
+
+    # ---- kernel arm: inputs resident in HBM --------------------------------------------------
+    nnz = [int(ops.build_csr(ei, n, transpose=False).rowptr[-1].item()) for ei in eis_d]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE = {}
+    ops.CALLS["n"] = 0
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(xs_d, eis_d)
+    ev1.record()
+    barrier()
+    prof, ops.PROFILE = ops.PROFILE, None
+    launches = ops.CALLS["n"]
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms.item()) / args.steps
+    units_per_step = e * t_steps * world
+    value = units_per_step / (ms_step * 1e-3)
+
+    # ---- live per-kernel timing and roofline of the dominant kernel ---------------------------
+    kt = {k: [s.elapsed_time(t) for s, t in v] for k, v in prof.items()}
+    share = {k: sum(v) / (ms_step * args.steps) for k, v in kt.items()}
+    h = w.heads
+    mean_nnz = sum(nnz) / len(nnz)
+    bytes_fwd = mean_nnz * (2 * hdim * 4 + 4) + n * (2 * hdim * 4 + 8 * h + 8)
+    bytes_bwd = mean_nnz * (4 * hdim * 4 + 12) + n * (6 * hdim * 4 + 8 * h + 8)
+    peak, peak_src = peaks()
+    t_fwd = statistics.mean(kt["geo_attn_fwd"]) * 1e-3
+    t_bwd = statistics.mean(kt["geo_attn_bwd"]) * 1e-3
+    ach_bwd = bytes_bwd / t_bwd / 1e9
+    ach_fwd = bytes_fwd / t_fwd / 1e9
+    roofline = {"kernel": "geo_attn_bwd (row pass + column pass)", "bound": "hbm", "achieved": ach_bwd, "peak": peak,
+                "unit": "GB/s", "frac": ach_bwd / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_bwd, "avg_launch_ms": t_bwd * 1e3,
+                "geo_attn_fwd": {"achieved": ach_fwd, "frac": ach_fwd / peak, "algorithmic_bytes_per_launch": bytes_fwd,
+                                 "avg_launch_ms": t_fwd * 1e3},
+                "share_of_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(args.workload, {}).get("geo_attn_bwd")
+        except Exception:
+            pass
+
+    # ---- e2e arm: host buffers, H2D copies and D2H loss read inside the timed region ----------
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(x.numel() * 4 for x in xs_h) + sum(ei.numel() * 8 for ei in eis_h)
+
+        def e2e_step():
+            xs = [x.to(dev, non_blocking=True) for x in xs_h]
+            eis = [ei.to(dev, non_blocking=True) for ei in eis_h]
+            return float(step(xs, eis).item())
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        g1.record()
+        barrier()
+        ems = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": units_per_step / (float(ems.item()) / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": float(ems.item()) / args.steps,
+               "wall_ms_per_step": (time.perf_counter() - t0) / args.steps * 1e3}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on this box's host cores ------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cstep, cunits, cdesc = cpu_sample_step_factory(w, args.metric)
+        t0 = time.perf_counter()
+        cstep()
+        cdt = time.perf_counter() - t0
+        cpu = {"value": cunits / cdt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": cdesc,
+               "seconds": cdt}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w.name, "nodes": n, "edges_per_snapshot": e, "snapshots": t_steps,
+                           "hidden": hdim, "heads": h, "distance_metric": args.metric,
+                           "parallelism": f"dp{world} (one sequence per GPU, NCCL grad all-reduce)",
+                           "memory_bank": not args.no_bank,
+                           "l2": "inputs larger than L2 (each step streams > 10 GB)"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

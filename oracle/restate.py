@@ -194,7 +194,7 @@ def time_bias(time_stamps: torch.Tensor, sd, num_heads: int) -> torch.Tensor:
         tn = torch.zeros_like(tv)
     mu = sd["time_encoding.basis_mu"]
     sigma = sd["time_encoding.basis_sigma"]
-    if float(sigma.min()) < 1e-7:
+    if float(sigma.detach().min()) < 1e-7:
         sigma = torch.clamp(sigma, min=1e-7)
     expo = -((tn.unsqueeze(-1) - mu) ** 2 / (2 * sigma ** 2))
     expo = torch.clamp(expo, min=-88.0, max=88.0)

@@ -11,7 +11,8 @@ from .layers import (AsymmetricTemporalAttention, GeometricAttention, TAGANGraph
                      TemporalSkipConnection, TimeEncoding)
 
 from .memory_bank import NodeMemoryBank  # noqa: F401,E402
+from .model import TAGANLayer, patch  # noqa: F401,E402
 
-__all__ = ["NodeMemoryBank", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
+__all__ = ["NodeMemoryBank", "TAGANLayer", "patch", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
            "TemporalGRUCell", "TemporalEvolutionLayer", "TemporalSkipConnection", "TemporalGatingUnit",
            "TemporalPropagation"]

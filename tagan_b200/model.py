@@ -1,0 +1,75 @@
+"""The "TAGAN layer" the benchmark times and the hook that swaps the B200
+layers into a reference ``TAGAN`` model.
+
+``TAGANLayer`` = one geometric attention layer applied to every snapshot (CSR built on device per
+snapshot) + the runnable propagation core (evolution -> skip -> projection) + temporal attention
+over the snapshot axis + memory-bank gather/update per snapshot.  Everything runs in
+libtagan_b200; torch only carries tensors between the calls and drives autograd.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import AsymmetricTemporalAttention, TAGANGraphAttention, TemporalPropagation
+from .memory_bank import NodeMemoryBank
+
+
+class TAGANLayer(nn.Module):
+    def __init__(self, hidden_dim: int, num_heads: int, distance_metric: str = "euclidean", dropout: float = 0.0,
+                 temporal_window_size: int = 3, window_size: int = 5, causal_attention: bool = False):
+        super().__init__()
+        self.hidden_dim, self.num_heads = hidden_dim, num_heads
+        self.geometric = TAGANGraphAttention(hidden_dim, num_heads, dropout, distance_metric)
+        self.geometric.validate_indices = False
+        self.propagation = TemporalPropagation(hidden_dim, hidden_dim, dropout, window_size=temporal_window_size)
+        self.temporal_attention = AsymmetricTemporalAttention(hidden_dim, num_heads, dropout, causal=causal_attention,
+                                                              asymmetric_window_size=window_size)
+
+    def forward(self, xs: Sequence[torch.Tensor], edge_indices: Sequence, time_stamps: Optional[torch.Tensor] = None,
+                bank: Optional[NodeMemoryBank] = None, node_ids: Optional[Sequence[torch.Tensor]] = None):
+        """xs: T tensors ``[N,H]``; edge_indices: T ``[2,E]`` int64 tensors (or prebuilt ``ops.CSR``);
+        time_stamps ``[N,T]``.  Returns ``[N,T,H]``."""
+        geo = [self.geometric(x, ei) for x, ei in zip(xs, edge_indices)]
+        prop = self.propagation.forward_core(geo, time_stamps)                      # [T,N,H]
+        if bank is not None:
+            t_steps, n = prop.shape[0], prop.shape[1]
+            for t in range(t_steps):
+                ids = node_ids[t] if node_ids is not None else torch.arange(n, dtype=torch.int32, device=prop.device)
+                bank.get_states(ids)                                                 # previous states (gather)
+                bank.update(ids, prop[t].detach(), t)                                # scatter-update / decay / prune
+        return self.temporal_attention(list(prop.unbind(0)), time_stamps=time_stamps)
+
+
+def patch(model: nn.Module) -> nn.Module:
+    """Swap the hot-path layers of a reference ``TAGAN`` for the B200 ones, in place.
+
+    Keeps every parameter (state_dict keys are identical) and the reference's own ``forward``:
+    ``model.geometric_attention_layers[i]``, ``model.temporal_propagation``, ``model.temporal_attention``
+    and ``model.memory_bank`` (model.py:57-61, 73-113 of the reference) are replaced.
+    """
+    cfg = model.config
+    dev = next(model.parameters()).device
+    metric = "scaled_dot_product" if cfg.learnable_distance else "euclidean"       # reference model.py:80
+    new_layers = nn.ModuleList()
+    for old in model.geometric_attention_layers:
+        new = TAGANGraphAttention(cfg.hidden_dim, cfg.num_heads, cfg.dropout, metric, cfg.use_layer_norm,
+                                  cfg.learnable_distance)
+        new.load_state_dict(old.state_dict())
+        new_layers.append(new.to(dev))
+    model.geometric_attention_layers = new_layers
+    tp = TemporalPropagation(cfg.hidden_dim, cfg.hidden_dim, cfg.dropout, cfg.time_aware, cfg.bidirectional,
+                             cfg.use_layer_norm, cfg.use_skip_connection, cfg.use_gating, cfg.temporal_window_size,
+                             cfg.aggregation_method, cfg.use_residual)
+    tp.load_state_dict(model.temporal_propagation.state_dict())
+    model.temporal_propagation = tp.to(dev)
+    ta = AsymmetricTemporalAttention(cfg.hidden_dim, cfg.num_heads, cfg.dropout, causal=cfg.causal_attention,
+                                     time_aware=True, use_layer_norm=cfg.use_layer_norm,
+                                     asymmetric_window_size=cfg.window_size,
+                                     relative_position_bias=cfg.asymmetric_temporal_bias)
+    ta.load_state_dict(model.temporal_attention.state_dict())
+    model.temporal_attention = ta.to(dev)
+    model.memory_bank = NodeMemoryBank(cfg.hidden_dim, decay_factor=0.8, max_inactivity=cfg.temporal_window_size,
+                                       device=dev)
+    return model

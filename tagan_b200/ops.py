@@ -19,8 +19,29 @@ METRIC_ID = {m: i for i, m in enumerate(METRICS)}
 # 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = 1xTF32 tcgen05
 GEMM_PRECISION = 0
 
-# number of libtagan_b200 kernel-launching calls made (bench.py reports launches from this)
+# number of libtagan_b200 kernels launched (bench.py reports `gpu_launches` from this)
 CALLS = {"n": 0}
+
+# When a dict, the named C calls are bracketed with CUDA events on the launching stream
+# (bench.py's live per-kernel timing); None = off.
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e.record(torch.cuda.current_stream())
+            PROFILE.setdefault(self.name, []).append((self.s, self.e))
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -116,10 +137,11 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int, transpose: bool = True, 
         perm_t = torch.empty(max(cap, 1), **i32)
     nbytes = lib.tagan_csr_workspace_bytes(e, num_nodes)
     ws = workspace(nbytes, dev)
-    rc = lib.tagan_csr_build(_ptr(ei) if e else None, e, num_nodes, _ptr(rowptr), _ptr(col), _ptr(row),
-                             _ptr(rowptr_t), _ptr(row_t), _ptr(perm_t), _ptr(status), _ptr(ws), ws.numel(), _stream())
+    with _timed("csr_build"):
+        rc = lib.tagan_csr_build(_ptr(ei) if e else None, e, num_nodes, _ptr(rowptr), _ptr(col), _ptr(row),
+                                 _ptr(rowptr_t), _ptr(row_t), _ptr(perm_t), _ptr(status), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "tagan_csr_build")
-    CALLS["n"] += 1
+    CALLS["n"] += 22 if transpose else 12
     if validate and int(status.item()) != 0:
         raise IndexError("edge_index out of range for num_nodes=%d" % num_nodes)
     return CSR(num_nodes, e, rowptr, col, row, rowptr_t, row_t, perm_t, status)
@@ -132,8 +154,9 @@ def gemm(op: int, m: int, n: int, k: int, a, lda, b, ldb, bias, c, ldc, accumula
     lib = _lib.load()
     nbytes = lib.tagan_gemm_workspace_bytes(op, m, n, k)
     ws = workspace(nbytes, c.device) if nbytes else None
-    rc = lib.tagan_gemm(op, m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(bias), _ptr(c), ldc, int(accumulate),
-                        GEMM_PRECISION, _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+    with _timed("gemm"):
+        rc = lib.tagan_gemm(op, m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(bias), _ptr(c), ldc, int(accumulate),
+                            GEMM_PRECISION, _ptr(ws), ws.numel() if ws is not None else 0, _stream())
     _lib.check(rc, "tagan_gemm")
     CALLS["n"] += 1
 
@@ -259,8 +282,9 @@ class _GeoAttnFn(torch.autograd.Function):
             attn = torch.zeros(max(csr.num_edges + csr.num_nodes, 1), heads, dtype=torch.float32, device=qkv.device)
         base = qkv2.data_ptr()
         q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
-        rc = lib.tagan_geo_attn_fwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), n, h, heads, metric,
-                                    _ptr(metric_param), _ptr(ctxv), _ptr(lse), _ptr(attn), _stream())
+        with _timed("geo_attn_fwd"):
+            rc = lib.tagan_geo_attn_fwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), n, h, heads, metric,
+                                        _ptr(metric_param), _ptr(ctxv), _ptr(lse), _ptr(attn), _stream())
         _lib.check(rc, "tagan_geo_attn_fwd")
         CALLS["n"] += 1
         ctx.save_for_backward(qkv2, metric_param, ctxv, lse)
@@ -289,9 +313,10 @@ class _GeoAttnFn(torch.autograd.Function):
         base, dbase = qkv2.data_ptr(), dqkv.data_ptr()
         q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
         dq, dk, dv = (C.c_void_p(dbase + i * h * 4) for i in range(3))
-        rc = lib.tagan_geo_attn_bwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.rowptr_t), _ptr(csr.row_t),
-                                    n, h, ctx.heads, ctx.metric, _ptr(metric_param), _ptr(ctxv), _ptr(lse), _ptr(dctx),
-                                    dq, dk, dv, three_h, _ptr(delta), _ptr(dp_ws), _ptr(dparam), _stream())
+        with _timed("geo_attn_bwd"):
+            rc = lib.tagan_geo_attn_bwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.rowptr_t), _ptr(csr.row_t),
+                                        n, h, ctx.heads, ctx.metric, _ptr(metric_param), _ptr(ctxv), _ptr(lse), _ptr(dctx),
+                                        dq, dk, dv, three_h, _ptr(delta), _ptr(dp_ws), _ptr(dparam), _stream())
         _lib.check(rc, "tagan_geo_attn_bwd")
         CALLS["n"] += 3 if want_dp else 2
         return dqkv, dparam, None, None, None, None
@@ -396,9 +421,10 @@ class _TAttnFn(torch.autograd.Function):
         mb, mh = (m.shape[0], m.shape[1]) if m is not None else (1, 1)
         base = qkv2.data_ptr()
         q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
-        rc = lib.tagan_tattn_fwd(q, k, v, ld, batch, t, h, heads, int(time_major), _ptr(bias_t), bstride,
-                                 _ptr(tmask.ts), tmask.flags, tmask.band, _ptr(tmask.allones_flag), _ptr(m), mb, mh,
-                                 _ptr(ctxv), _ptr(lse), _ptr(attn), _stream())
+        with _timed("tattn_fwd"):
+            rc = lib.tagan_tattn_fwd(q, k, v, ld, batch, t, h, heads, int(time_major), _ptr(bias_t), bstride,
+                                     _ptr(tmask.ts), tmask.flags, tmask.band, _ptr(tmask.allones_flag), _ptr(m), mb, mh,
+                                     _ptr(ctxv), _ptr(lse), _ptr(attn), _stream())
         _lib.check(rc, "tagan_tattn_fwd")
         CALLS["n"] += 1
         ctx.save_for_backward(qkv2, bias_c, bias_t, ctxv, lse)
@@ -430,10 +456,11 @@ class _TAttnFn(torch.autograd.Function):
         base, dbase = qkv2.data_ptr(), dqkv.data_ptr()
         q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
         dq, dk, dv = (C.c_void_p(dbase + i * h * 4) for i in range(3))
-        rc = lib.tagan_tattn_bwd(q, k, v, ld, batch, t, h, heads, int(time_major), _ptr(bias_c), _ptr(bias_t),
-                                 ctx.bstride, _ptr(tmask.ts), tmask.flags, tmask.band, _ptr(tmask.allones_flag),
-                                 _ptr(m), mb, mh, _ptr(ctxv), _ptr(lse), _ptr(dctx), dq, dk, dv, three_h,
-                                 _ptr(dbias), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+        with _timed("tattn_bwd"):
+            rc = lib.tagan_tattn_bwd(q, k, v, ld, batch, t, h, heads, int(time_major), _ptr(bias_c), _ptr(bias_t),
+                                     ctx.bstride, _ptr(tmask.ts), tmask.flags, tmask.band, _ptr(tmask.allones_flag),
+                                     _ptr(m), mb, mh, _ptr(ctxv), _ptr(lse), _ptr(dctx), dq, dk, dv, three_h,
+                                     _ptr(dbias), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
         _lib.check(rc, "tagan_tattn_bwd")
         CALLS["n"] += 2 if ws is not None else 1
         if dbias is not None:
