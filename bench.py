@@ -193,8 +193,8 @@ def run_ours(args):
     if not args.no_bank:
         bank = tagan_b200.NodeMemoryBank(hdim, 0.8, 3, device=dev, capacity=n)
         bank.check_range = False
-    params = [p for p in layer.parameters() if p.requires_grad]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev) if world > 1 else None
+    from tagan_b200.dist import GradBucket
+    bucket = GradBucket(list(layer.parameters())) if world > 1 else None
 
     def step(xs, eis):
         layer.zero_grad(set_to_none=True)
@@ -202,13 +202,7 @@ def run_ours(args):
         loss = out.square().mean()
         loss.backward()
         if world > 1:                       # data-parallel: one flat NCCL all-reduce of the gradients
-            off = 0
-            for p in params:
-                g = p.grad if p.grad is not None else torch.zeros_like(p)
-                flat[off:off + p.numel()].copy_(g.reshape(-1))
-                off += p.numel()
-            dist.all_reduce(flat)
-            flat.div_(world)
+            bucket.all_reduce(world)
         return loss
 
     def barrier():
