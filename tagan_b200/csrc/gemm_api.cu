@@ -7,9 +7,15 @@ int tagan_gemm_simt(int32_t op, int64_t M, int64_t N, int64_t K, const float* A,
                     int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, void* workspace,
                     size_t workspace_bytes, cudaStream_t st);
 
+size_t tagan_gemm_tc_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K);
+int tagan_gemm_tc(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                  int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 TAGAN_API size_t tagan_gemm_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k) {
   if (op < 0 || op > 2 || m < 0 || n < 0 || k < 0) return 0;
-  return tagan_gemm_simt_workspace_bytes(op, m, n, k);
+  size_t a = tagan_gemm_simt_workspace_bytes(op, m, n, k), b = tagan_gemm_tc_workspace_bytes(op, m, n, k);
+  return a > b ? a : b;
 }
 
 TAGAN_API int tagan_gemm(int32_t op, int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* B,
@@ -18,6 +24,10 @@ TAGAN_API int tagan_gemm(int32_t op, int64_t m, int64_t n, int64_t k, const floa
   if (op < 0 || op > 2 || m < 0 || n < 0 || k < 0 || !C || (k > 0 && (!A || !B))) return TAGAN_E_INVALID;
   if (precision < 0 || precision > 2) return TAGAN_E_INVALID;
   if (m == 0 || n == 0) return 0;
+  // tensor-core path: tiles are 128x128, so tiny problems (toy configs) stay on the FFMA kernel
+  if (precision > 0 && k > 0 && m * n >= 64 * 64)
+    return tagan_gemm_tc(op, m, n, k, A, lda, B, ldb, bias, C, ldc, accumulate, precision == 1 ? 3 : 1, workspace,
+                         workspace_bytes, as_stream(stream));
   return tagan_gemm_simt(op, m, n, k, A, lda, B, ldb, bias, C, ldc, accumulate, workspace, workspace_bytes,
                          as_stream(stream));
 }
