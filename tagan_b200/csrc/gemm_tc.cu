@@ -63,26 +63,28 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64): SWIZZLE_128B = 2 (K-major tiles),
+// SWIZZLE_128B_BASE32B = 1 (the only layout the hardware offers for MN-major tf32 operands).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
 // Canonical SWIZZLE_128B tile offsets (bytes) for a [128 mn x 32 k] fp32 tile.
 //   K-major : 8-row groups of 128-byte rows (k contiguous), 16-byte chunk index XOR (row % 8); SBO = 1024.
-//   MN-major: atoms of 8 k-rows x 128 bytes (32 mn contiguous), chunk XOR (k % 8); k-atoms 1024 B apart (SBO),
-//             mn-blocks of 32 floats 4096 B apart (LBO).
+//   MN-major (SWIZZLE_128B_BASE32B, Swizzle<2,5,2>): atoms of 4 k-rows x 128 bytes (32 mn contiguous), the
+//             32-byte chunk index XOR (k % 4); k-atoms 512 B apart (SBO), mn-blocks of 32 floats 4096 B apart (LBO).
 __device__ __forceinline__ uint32_t off_kmajor(int mn, int kchunk /*k/4*/) {
   return (uint32_t)((mn >> 3) * 1024 + (mn & 7) * 128 + ((kchunk ^ (mn & 7)) << 4));
 }
 __device__ __forceinline__ uint32_t off_mnmajor(int mnchunk /*mn/4*/, int k) {
-  return (uint32_t)((mnchunk >> 3) * 4096 + (k >> 3) * 1024 + (k & 7) * 128 + (((mnchunk & 7) ^ (k & 7)) << 4));
+  const int c16 = mnchunk & 7;                     // 16-byte chunk inside the 128-byte row
+  return (uint32_t)((mnchunk >> 3) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((c16 >> 1) ^ (k & 3)) << 5) | ((c16 & 1) << 4)));
 }
 
 __device__ __forceinline__ void split_store(char* hi_tile, char* lo_tile, uint32_t off, float4 v) {
@@ -215,9 +217,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       // per k-step (8 tf32 = 32 bytes) descriptor advance: +32 B inside the swizzle row (K-major),
-      // +1024 B = next k-atom (MN-major)
+      // +1024 B = two 4-row k-atoms further (MN-major)
       const uint32_t a_step = p.a_mn_major ? 1024u : 32u, b_step = p.b_mn_major ? 1024u : 32u;
       const uint32_t a_lbo = p.a_mn_major ? 4096u : 16u, b_lbo = p.b_mn_major ? 4096u : 16u;
+      const uint32_t a_sbo = p.a_mn_major ? 512u : 1024u, b_sbo = p.b_mn_major ? 512u : 1024u;
+      const uint32_t a_lay = p.a_mn_major ? 1u : 2u, b_lay = p.b_mn_major ? 1u : 2u;
       for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
         const int64_t kbeg = (int64_t)ks * p.k_per_split;
@@ -232,10 +236,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
           const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t da_hi = make_desc(sbase + kk * a_step, a_lbo, 1024);
-            const uint64_t da_lo = make_desc(sbase + TILE_BYTES + kk * a_step, a_lbo, 1024);
-            const uint64_t db_hi = make_desc(sbase + 2 * TILE_BYTES + kk * b_step, b_lbo, 1024);
-            const uint64_t db_lo = make_desc(sbase + 3 * TILE_BYTES + kk * b_step, b_lbo, 1024);
+            const uint64_t da_hi = make_desc(sbase + kk * a_step, a_lbo, a_sbo, a_lay);
+            const uint64_t da_lo = make_desc(sbase + TILE_BYTES + kk * a_step, a_lbo, a_sbo, a_lay);
+            const uint64_t db_hi = make_desc(sbase + 2 * TILE_BYTES + kk * b_step, b_lbo, b_sbo, b_lay);
+            const uint64_t db_lo = make_desc(sbase + 3 * TILE_BYTES + kk * b_step, b_lbo, b_sbo, b_lay);
             if (p.passes == 3) {
               umma_tf32(tmem_d, da_lo, db_hi, p.idesc, accum);   // small terms first
               umma_tf32(tmem_d, da_hi, db_lo, p.idesc, 1);

@@ -17,7 +17,7 @@ METRICS = ["scaled_dot_product", "dot_product", "cosine_similarity", "euclidean"
 METRIC_ID = {m: i for i, m in enumerate(METRICS)}
 
 # 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = 1xTF32 tcgen05
-GEMM_PRECISION = 0
+GEMM_PRECISION = 1
 
 # number of libtagan_b200 kernels launched (bench.py reports `gpu_launches` from this)
 CALLS = {"n": 0}
