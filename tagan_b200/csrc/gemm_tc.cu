@@ -4,15 +4,15 @@
 //                            TN: A[K,M],B[K,N] (dW = dY^T.X, split-K, fixed-order reduction)
 //
 // The reference's projections are fp32 nn.Linear; parity is rtol 1e-4 / atol 1e-5, which plain TF32
-// (10-bit mantissa) misses.  Every fp32 operand is split on the fly into hi = top 19 bits (exactly
-// representable in TF32) and lo = x - hi (exact in fp32), and D += Ahi.Bhi + Ahi.Blo + Alo.Bhi is
+// (10-bit mantissa) misses.  Every fp32 operand is split on the fly into hi = rn_tf32(x) and lo = rn_tf32(x - hi) (both exactly
+// representable in TF32, unbiased), and D += Ahi.Bhi + Ahi.Blo + Alo.Bhi is
 // accumulated in fp32 in TMEM (the dropped lo.lo term is ~2^-22 relative).
 //
 // Persistent, warp-specialised CTA (one per SM), 128x128 output tiles, BK = 32 floats = one 128-byte
 // swizzle row, 3-stage smem ring, 2 accumulator stages in TMEM (256 columns):
 //   warps 0-3   epilogue : tcgen05.ld 32 lanes x 32 columns -> +bias/+C -> global (row-contiguous 128 B runs)
 //   warp  4     MMA      : one elected thread issues tcgen05.mma.kind::tf32 (3 per k-step) and tcgen05.commit
-//   warps 5-12  producers: coalesced 128-bit global loads -> hi/lo split -> st.shared into the canonical
+//   warps 5-20  producers (two groups of 8 warps alternating k-blocks): coalesced 128-bit global loads -> hi/lo split -> st.shared into the canonical
 //                          SWIZZLE_128B UMMA layouts (K-major or MN-major, so no transposes are ever
 //                          materialised) -> fence.proxy.async -> mbarrier arrive
 // With K <= 512 and N <= 768 these GEMMs sit at ~140 flop/byte even at 3x work, i.e. they are HBM-bound
@@ -26,12 +26,17 @@ constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
 constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB (A and B tiles have the same size)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
 constexpr int MMA_WARP = EPI_WARPS;                     // warp 4
 constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;   // 416
 constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int PROD_GROUPS = 2;                          // groups alternate k-blocks: TLP hides the load latency
+constexpr int GROUP_WARPS = PROD_WARPS / PROD_GROUPS;   // 8 warps = 256 threads per group
 constexpr int TMEM_COLS = ACC_STAGES * BN;              // 256
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr int EPI_PITCH = 36;                           // floats; 144-byte rows keep the staging tile conflict-free
+constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH * 4;     // per epilogue warp
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ +
+                              (size_t)EPI_WARPS * EPI_STAGE_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,13 +92,17 @@ __device__ __forceinline__ uint32_t off_mnmajor(int mnchunk /*mn/4*/, int k) {
   return (uint32_t)((mnchunk >> 3) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((c16 >> 1) ^ (k & 3)) << 5) | ((c16 & 1) << 4)));
 }
 
+// Round-to-nearest TF32 (unbiased: a truncating split would accumulate a systematic error ~K*2^-22).
+// Same result as cvt.rna.tf32.f32 (nearest, ties away from zero) with two full-rate integer ops.
+__device__ __forceinline__ float tf32_rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+// hi = rn_tf32(x), lo = rn_tf32(x - hi): both exactly representable, so the tensor core's own
+// fp32->tf32 conversion is the identity and every product is exact.
 __device__ __forceinline__ void split_store(char* hi_tile, char* lo_tile, uint32_t off, float4 v) {
   float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+  h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+  l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
   *reinterpret_cast<float4*>(hi_tile + off) = h;
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
@@ -140,10 +149,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PROD_WARPS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], GROUP_WARPS); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     fence_barrier_init();
   }
@@ -160,56 +170,81 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
 
   if (warp > MMA_WARP) {
     // ============================== producers ==============================
-    const int pt = threadIdx.x - (MMA_WARP + 1) * 32;      // 0..255
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int nt = (int)(w % p.tiles_n);
-      const int mt = (int)((w / p.tiles_n) % p.tiles_m);
-      const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
+    // 512 threads share the 2048 float4 chunks of a k-block (A tile + B tile).  Global loads run two
+    // k-blocks ahead of the shared-memory stores through a 3-deep register ring (across tile
+    // boundaries too), so ~64 KB per SM are in flight and the A stream is not latency-bound.
+    // Two groups of 8 warps; group g produces k-blocks g, g+2, g+4, ... of this CTA's sequence (across
+    // tile boundaries).  A group issues its 8 loads per thread, waits for the stage to be free, splits and
+    // stores, then arrives on the stage's full barrier.  While one group waits on HBM the other one stores,
+    // so two k-blocks (64 KB) are always in flight without any register-resident prefetch ring.
+    const int group = (warp - (MMA_WARP + 1)) / GROUP_WARPS;
+    const int pt = (threadIdx.x - (MMA_WARP + 1) * 32) % (GROUP_WARPS * 32);      // 0..255 inside the group
+    const int kb_per_split = (int)(p.k_per_split / BK);
+    const int kb_total = (int)((p.K + BK - 1) / BK);
+    const int nwork = (int)num_work;
+    // chunk i (0..3) of a tile for this thread: K-major: row (pt>>3)+32i, 16-byte k-chunk pt&7;
+    // MN-major: k row (pt>>5)+8i, 16-byte mn-chunk pt&31.  smem / global offsets are affine in i.
+    const uint32_t sa0 = p.a_mn_major ? off_mnmajor(pt & 31, pt >> 5) : off_kmajor(pt >> 3, pt & 7);
+    const uint32_t sb0 = 2u * TILE_BYTES + (p.b_mn_major ? off_mnmajor(pt & 31, pt >> 5) : off_kmajor(pt >> 3, pt & 7));
+    const uint32_t sas = p.a_mn_major ? 1024u : 4096u, sbs = p.b_mn_major ? 1024u : 4096u;
+    const int64_t ga0 = p.a_mn_major ? (int64_t)(pt >> 5) * p.lda + (pt & 31) * 4 : (int64_t)(pt >> 3) * p.lda + (pt & 7) * 4;
+    const int64_t gb0 = p.b_mn_major ? (int64_t)(pt >> 5) * p.ldb + (pt & 31) * 4 : (int64_t)(pt >> 3) * p.ldb + (pt & 7) * 4;
+    const int64_t gas = (p.a_mn_major ? 8 : 32) * p.lda, gbs = (p.b_mn_major ? 8 : 32) * p.ldb;
+    const int64_t a_kstep = p.a_mn_major ? (int64_t)BK * p.lda : BK;      // elements per k-block
+    const int64_t b_kstep = p.b_mn_major ? (int64_t)BK * p.ldb : BK;
+    int w = blockIdx.x, kb = 0, nkb = 0, mt = 0, nt = 0, kbeg = 0;
+    auto setup = [&]() {
+      if (w >= nwork) { nkb = 0; return; }
+      nt = w % p.tiles_n;
+      const int q = w / p.tiles_n;
+      mt = q % p.tiles_m;
+      kbeg = (q / p.tiles_m) * kb_per_split;
+      const int rem = kb_total - kbeg;
+      nkb = rem < kb_per_split ? rem : kb_per_split;
+      kb = 0;
+    };
+    auto advance = [&]() {
+      if (++kb >= nkb) { w += gridDim.x; setup(); }
+    };
+    setup();
+    int j = 0;                                            // index in the CTA's k-block sequence
+    for (int g = 0; g < group && w < nwork; ++g) { advance(); ++j; }
+    while (w < nwork) {
       const int64_t m0 = (int64_t)mt * BM, n0 = (int64_t)nt * BN;
-      const int64_t kbeg = (int64_t)ks * p.k_per_split;
-      const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
-      for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        char* st = reinterpret_cast<char*>(smem) + (size_t)stage * STAGE_BYTES;
-        char* a_hi = st, *a_lo = st + TILE_BYTES, *b_hi = st + 2 * TILE_BYTES, *b_lo = st + 3 * TILE_BYTES;
-        // 128 x 32 floats = 1024 float4 per operand tile, 4 per producer thread
-        if (!p.a_mn_major) {
+      const int64_t k0 = (int64_t)(kbeg + kb) * BK;
+      const int64_t klim = (int64_t)(kbeg + nkb) * BK < p.K ? (int64_t)(kbeg + nkb) * BK : p.K;
+      float4 r[8];
+      if (p.a_vec && p.b_vec && m0 + BM <= p.M && n0 + BN <= p.N && k0 + BK <= klim) {
+        const float* pa = p.A + (p.a_mn_major ? m0 : m0 * p.lda) + (int64_t)(kbeg + kb) * a_kstep + ga0;
+        const float* pb = p.B + (p.b_mn_major ? n0 : n0 * p.ldb) + (int64_t)(kbeg + kb) * b_kstep + gb0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (pt >> 3) + 32 * i, c = pt & 7;      // row, 16-byte k-chunk
-            float4 v = load4(p.A, m0 + r, p.lda, k0 + c * 4, p.M, kend, p.a_vec);
-            split_store(a_hi, a_lo, off_kmajor(r, c), v);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int k = (pt >> 5) + 8 * i, c = pt & 31;      // k row, 16-byte mn-chunk
-            float4 v = load4(p.A, k0 + k, p.lda, m0 + c * 4, kend, p.M, p.a_vec);
-            split_store(a_hi, a_lo, off_mnmajor(c, k), v);
-          }
+        for (int i = 0; i < 4; ++i) {
+          r[i] = __ldg(reinterpret_cast<const float4*>(pa + i * gas));
+          r[4 + i] = __ldg(reinterpret_cast<const float4*>(pb + i * gbs));
         }
-        if (!p.b_mn_major) {
+      } else {             // edge tiles: guarded element-wise loads with zero fill
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (pt >> 3) + 32 * i, c = pt & 7;
-            float4 v = load4(p.B, n0 + r, p.ldb, k0 + c * 4, p.N, kend, p.b_vec);
-            split_store(b_hi, b_lo, off_kmajor(r, c), v);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int k = (pt >> 5) + 8 * i, c = pt & 31;
-            float4 v = load4(p.B, k0 + k, p.ldb, n0 + c * 4, kend, p.N, p.b_vec);
-            split_store(b_hi, b_lo, off_mnmajor(c, k), v);
-          }
+        for (int i = 0; i < 4; ++i) {
+          if (!p.a_mn_major) r[i] = load4(p.A, m0 + (pt >> 3) + 32 * i, p.lda, k0 + (pt & 7) * 4, p.M, klim, p.a_vec);
+          else r[i] = load4(p.A, k0 + (pt >> 5) + 8 * i, p.lda, m0 + (pt & 31) * 4, klim, p.M, p.a_vec);
+          if (!p.b_mn_major) r[4 + i] = load4(p.B, n0 + (pt >> 3) + 32 * i, p.ldb, k0 + (pt & 7) * 4, p.N, klim, p.b_vec);
+          else r[4 + i] = load4(p.B, k0 + (pt >> 5) + 8 * i, p.ldb, n0 + (pt & 31) * 4, klim, p.N, p.b_vec);
         }
-        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      const int stage = j % STAGES;
+      mbar_wait(&empty_bar[stage], ((j / STAGES) & 1) ^ 1);
+      char* st = reinterpret_cast<char*>(smem) + (size_t)stage * STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        split_store(st, st + TILE_BYTES, sa0 + i * sas, r[i]);
+        split_store(st, st + TILE_BYTES, sb0 + i * sbs, r[4 + i]);
+      }
+      fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      // skip the other groups' k-blocks
+      for (int g = 0; g < PROD_GROUPS && w < nwork; ++g) advance();
+      j += PROD_GROUPS;
     }
   } else if (warp == MMA_WARP) {
     // ============================== MMA issuer ==============================
@@ -266,7 +301,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
       const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
       const int64_t kbeg = (int64_t)ks * p.k_per_split;
       const bool has_k = kbeg < p.K;
-      const int64_t row = (int64_t)mt * BM + warp * 32 + lane;
       const int64_t n0 = (int64_t)nt * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -292,40 +326,42 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
-        if (row < p.M) {
-          const int64_t c0 = n0 + cc * 32;
-          float* orow = out + row * ldo + c0;
-          const bool direct = p.partial == nullptr;
+        // registers (lane = row, 32 consecutive columns) -> padded smem tile -> row-contiguous 128-byte stores
+        float* stg = epi_stage + warp * (32 * EPI_PITCH);
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
-            if (c0 + j + 3 < p.N && p.c_vec) {
-              if (direct) {
-                if (p.bias) {
-                  float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-                  v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                }
-                if (p.accumulate) {
-                  float4 o4 = *reinterpret_cast<const float4*>(orow + j);
-                  v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
-                }
-              }
-              *reinterpret_cast<float4*>(orow + j) = v;
-            } else {
-              const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+        const int64_t c0 = n0 + cc * 32 + (lane & 7) * 4;
+        const bool direct = p.partial == nullptr;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (direct && p.bias) {
+          if (c0 < p.N) b4.x = p.bias[c0];
+          if (c0 + 1 < p.N) b4.y = p.bias[c0 + 1];
+          if (c0 + 2 < p.N) b4.z = p.bias[c0 + 2];
+          if (c0 + 3 < p.N) b4.w = p.bias[c0 + 3];
+        }
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (c0 + j + q < p.N) {
-                  float x = vv[q];
-                  if (direct) {
-                    if (p.bias) x += p.bias[c0 + j + q];
-                    if (p.accumulate) x += orow[j + q];
-                  }
-                  orow[j + q] = x;
-                }
-              }
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3);
+          const int64_t grow = (int64_t)mt * BM + warp * 32 + rr;
+          if (grow >= p.M || c0 >= p.N) continue;
+          float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + (lane & 7) * 4);
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          float* orow = out + grow * ldo + c0;
+          if (c0 + 3 < p.N && p.c_vec) {
+            if (direct && p.accumulate) {
+              float4 o4 = *reinterpret_cast<const float4*>(orow);
+              v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
             }
+            *reinterpret_cast<float4*>(orow) = v;
+          } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (c0 + q < p.N) orow[q] = (direct && p.accumulate) ? orow[q] + vv[q] : vv[q];
           }
         }
       }
