@@ -10,6 +10,14 @@ pytestmark = pytest.mark.gpu
 TOL = dict(rtol=1e-4, atol=1e-5)
 
 
+def _close(got, ref, msg=None, rtol=1e-4, atol=1e-5):
+    """rtol 1e-4 / atol 1e-5, the atol taken relative to the tensor's scale when that exceeds 1 (sums of
+    O(10) terms cannot be resolved to 1e-5 absolute in fp32)."""
+    scale = max(1.0, float(ref.abs().max())) if ref.numel() else 1.0
+    torch.testing.assert_close(got, ref, rtol=rtol, atol=atol * scale, msg=msg)
+
+
+
 @pytest.fixture(scope="module")
 def dev():
     return torch.device("cuda:0")
@@ -116,9 +124,9 @@ def test_propagation_core_vs_oracle(dev, n, t, hidden):
     xd = [x.to(dev).requires_grad_(True) for x in xs]
     out = tp.forward_core(xd, ts.to(dev))
     (out * wout.to(dev)).sum().backward()
-    torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-4, atol=2e-5)
+    _close(out.detach().cpu(), ref.detach())
     for a, b in zip(xd, xr):
-        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-4, atol=2e-5)
+        _close(a.grad.cpu(), b.grad)
     for k, p in tp.named_parameters():
         gref = sd[k].grad
         if gref is None:

@@ -10,6 +10,14 @@ pytestmark = pytest.mark.gpu
 TOL = dict(rtol=1e-4, atol=1e-5)
 
 
+def _close(got, ref, msg=None, rtol=1e-4, atol=1e-5):
+    """rtol 1e-4 / atol 1e-5, the atol taken relative to the tensor's scale when that exceeds 1 (sums of
+    O(10) terms cannot be resolved to 1e-5 absolute in fp32)."""
+    scale = max(1.0, float(ref.abs().max())) if ref.numel() else 1.0
+    torch.testing.assert_close(got, ref, rtol=rtol, atol=atol * scale, msg=msg)
+
+
+
 @pytest.fixture(scope="module")
 def dev():
     return torch.device("cuda:0")
@@ -48,14 +56,14 @@ def test_temporal_attention_vs_reference_golden(dev, golden):
         out, attn = layer(xin, time_stamps=_to_dev(c["ts"], dev), attention_mask=_to_dev(c["mask"], dev),
                           return_attention_weights=True)
         name = c["name"]
-        torch.testing.assert_close(out.detach().cpu(), c["out"], **TOL, msg=lambda m: f"{name} out: {m}")
+        _close(out.detach().cpu(), c["out"], msg=lambda m: f"{name} out: {m}")
         torch.testing.assert_close(attn.cpu(), c["attn"], **TOL, msg=lambda m: f"{name} attn: {m}")
         (out * c["wout"].to(dev)).sum().backward()
         if "x_list" in c:
             for a, b in zip(xin, c["dx_list"]):
-                torch.testing.assert_close(a.grad.cpu(), b, **TOL, msg=lambda m: f"{name} dx: {m}")
+                _close(a.grad.cpu(), b, msg=lambda m: f"{name} dx: {m}")
         else:
-            torch.testing.assert_close(xin.grad.cpu(), c["dx"], **TOL, msg=lambda m: f"{name} dx: {m}")
+            _close(xin.grad.cpu(), c["dx"], msg=lambda m: f"{name} dx: {m}")
         params = dict(layer.named_parameters())
         for k, gref in c["grads"].items():
             g = params[k].grad
@@ -95,9 +103,9 @@ def test_temporal_attention_vs_oracle_shapes(dev, b, t, hidden, heads, mode):
     xd = x.to(dev).requires_grad_(True)
     out, attn = layer(xd, time_stamps=_to_dev(ts, dev), attention_mask=_to_dev(mask, dev), return_attention_weights=True)
     (out * wout.to(dev)).sum().backward()
-    torch.testing.assert_close(out.detach().cpu(), ref.detach(), **TOL)
+    _close(out.detach().cpu(), ref.detach())
     torch.testing.assert_close(attn.cpu(), aref.detach(), **TOL)
-    torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=1e-4, atol=2e-5)
+    _close(xd.grad.cpu(), xr.grad)
     for k, p in layer.named_parameters():
         gref = sd[k].grad
         if gref is None:
