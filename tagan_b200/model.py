@@ -70,6 +70,7 @@ def patch(model: nn.Module) -> nn.Module:
                                      relative_position_bias=cfg.asymmetric_temporal_bias)
     ta.load_state_dict(model.temporal_attention.state_dict())
     model.temporal_attention = ta.to(dev)
-    model.memory_bank = NodeMemoryBank(cfg.hidden_dim, decay_factor=0.8, max_inactivity=cfg.temporal_window_size,
-                                       device=dev)
+    if dev.type == "cuda":      # (on CPU only the module swap is done; the kernels need a CUDA device to run)
+        model.memory_bank = NodeMemoryBank(cfg.hidden_dim, decay_factor=0.8, max_inactivity=cfg.temporal_window_size,
+                                           device=dev)
     return model
