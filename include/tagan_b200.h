@@ -71,6 +71,17 @@ int tagan_csr_build(const int64_t* edge_index, int64_t num_edges, int32_t num_no
                     int32_t* status, void* workspace, size_t workspace_bytes,
                     tagan_stream_t stream);
 
+/* Node-partitioned variant (single large graph): this rank owns the query rows
+ * [row_begin, row_begin+num_rows); edges whose row lies elsewhere are skipped.  rowptr[num_rows+1], row[]
+ * hold LOCAL row ids, col[] GLOBAL node ids (self loop of local row i = row_begin+i); the transposed CSR is
+ * indexed by global source node (rowptr_t[num_nodes+1]) with local row ids in row_t. */
+int tagan_csr_build_part(const int64_t* edge_index, int64_t num_edges, int32_t num_nodes,
+                         int32_t row_begin, int32_t num_rows,
+                         int32_t* rowptr, int32_t* col, int32_t* row,
+                         int32_t* rowptr_t, int32_t* row_t, int32_t* perm_t,
+                         int32_t* status, void* workspace, size_t workspace_bytes,
+                         tagan_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * (a2-a4) fused geometric attention over the CSR: per-entry per-head score from the
  * DistanceMetric, segment softmax over each row, weighted aggregation of V.  One warp per
@@ -100,6 +111,21 @@ int tagan_geo_attn_bwd(const float* Q, const float* K, const float* V, int64_t l
                        const float* dctx, float* dQ, float* dK, float* dV, int64_t ldd,
                        float* delta_ws, float* dparam_ws, float* dparam,
                        tagan_stream_t stream);
+
+/* Rectangular forms for the node-partitioned graph: Q/ctx/dQ have n_rows LOCAL rows (stride ldq/lddq),
+ * K/V and dK/dV have n_src GLOBAL rows (stride ldkv/lddkv) -- K|V is the all-gathered projection, dK|dV
+ * the partial sums that are reduce-scattered afterwards. */
+int tagan_geo_attn_fwd_part(const float* Q, int64_t ldq, const float* K, const float* V, int64_t ldkv,
+                            const int32_t* rowptr, const int32_t* col, int32_t n_rows,
+                            int32_t hidden, int32_t heads, int32_t metric, const float* metric_param,
+                            float* ctx, float* lse, float* attn, tagan_stream_t stream);
+int tagan_geo_attn_bwd_part(const float* Q, int64_t ldq, const float* K, const float* V, int64_t ldkv,
+                            const int32_t* rowptr, const int32_t* col,
+                            const int32_t* rowptr_t, const int32_t* row_t,
+                            int32_t n_rows, int32_t n_src, int32_t hidden, int32_t heads, int32_t metric,
+                            const float* metric_param, const float* ctx, const float* lse,
+                            const float* dctx, float* dQ, int64_t lddq, float* dK, float* dV, int64_t lddkv,
+                            float* delta_ws, float* dparam_ws, float* dparam, tagan_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Row-wise building blocks shared by all layers (the reference uses nn.LayerNorm eps=1e-5,

@@ -107,28 +107,37 @@ __global__ void fill_i32(int* p, int v, int64_t n) {
   if (i < n) p[i] = v;
 }
 
-__global__ void count_rows(const int64_t* __restrict__ ei, int64_t E, int n, int* __restrict__ cnt, int* __restrict__ status) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  int r, c;
-  if (norm_index(ei[e], n, &r) && norm_index(ei[E + e], n, &c)) atomicAdd(&cnt[r], 1);
-  else *status = 1;
-}
-
-// bucket layout: position off[r] holds the self loop, the rest is filled through cursor[r] (starts at 1)
-__global__ void place_self_loops(const int* __restrict__ off, int* __restrict__ bucket, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) bucket[off[i]] = i;
-}
-
-__global__ void scatter_edges(const int64_t* __restrict__ ei, int64_t E, int n, const int* __restrict__ off,
-                              int* __restrict__ cursor, int* __restrict__ bucket) {
+// rows outside [row_begin, row_begin + nrows) belong to another partition and are skipped silently
+__global__ void count_rows(const int64_t* __restrict__ ei, int64_t E, int n, int row_begin, int nrows,
+                           int* __restrict__ cnt, int* __restrict__ status) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int r, c;
   if (norm_index(ei[e], n, &r) && norm_index(ei[E + e], n, &c)) {
-    int p = atomicAdd(&cursor[r], 1);
-    bucket[off[r] + p] = c;
+    r -= row_begin;
+    if (r >= 0 && r < nrows) atomicAdd(&cnt[r], 1);
+  } else {
+    *status = 1;
+  }
+}
+
+// bucket layout: position off[r] holds the self loop, the rest is filled through cursor[r] (starts at 1)
+__global__ void place_self_loops(const int* __restrict__ off, int* __restrict__ bucket, int n, int row_begin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bucket[off[i]] = row_begin + i;
+}
+
+__global__ void scatter_edges(const int64_t* __restrict__ ei, int64_t E, int n, int row_begin, int nrows,
+                              const int* __restrict__ off, int* __restrict__ cursor, int* __restrict__ bucket) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int r, c;
+  if (norm_index(ei[e], n, &r) && norm_index(ei[E + e], n, &c)) {
+    r -= row_begin;
+    if (r >= 0 && r < nrows) {
+      int p = atomicAdd(&cursor[r], 1);
+      bucket[off[r] + p] = c;
+    }
   }
 }
 
@@ -285,10 +294,13 @@ TAGAN_API size_t tagan_csr_workspace_bytes(int64_t num_edges, int32_t num_nodes)
   return ws_layout(num_edges, num_nodes).total;
 }
 
-TAGAN_API int tagan_csr_build(const int64_t* edge_index, int64_t E, int32_t N, int32_t* rowptr, int32_t* col,
-                              int32_t* row, int32_t* rowptr_t, int32_t* row_t, int32_t* perm_t, int32_t* status,
-                              void* workspace, size_t workspace_bytes, tagan_stream_t stream) {
-  if (E < 0 || N < 0 || !rowptr || !col || !row || !status || (E > 0 && !edge_index)) return TAGAN_E_INVALID;
+TAGAN_API int tagan_csr_build_part(const int64_t* edge_index, int64_t E, int32_t N, int32_t row_begin, int32_t R,
+                                   int32_t* rowptr, int32_t* col, int32_t* row, int32_t* rowptr_t, int32_t* row_t,
+                                   int32_t* perm_t, int32_t* status, void* workspace, size_t workspace_bytes,
+                                   tagan_stream_t stream) {
+  if (E < 0 || N < 0 || R < 0 || row_begin < 0 || row_begin + (int64_t)R > N || !rowptr || !col || !row || !status ||
+      (E > 0 && !edge_index))
+    return TAGAN_E_INVALID;
   if (E + (int64_t)N >= 0x7fffffffLL) return TAGAN_E_UNSUPPORTED;
   const bool transpose = rowptr_t || row_t || perm_t;
   if (transpose && !(rowptr_t && row_t && perm_t)) return TAGAN_E_INVALID;
@@ -306,36 +318,45 @@ TAGAN_API int tagan_csr_build(const int64_t* edge_index, int64_t E, int32_t N, i
   int* scanws = (int*)(w + L.scan);
   const int TB = 256;
   cudaMemsetAsync(status, 0, sizeof(int), st);
-  if (N == 0) {
+  if (transpose) cudaMemsetAsync(rowptr_t, 0, sizeof(int) * ((size_t)N + 1), st);
+  if (R == 0) {
     cudaMemsetAsync(rowptr, 0, sizeof(int), st);
-    if (transpose) cudaMemsetAsync(rowptr_t, 0, sizeof(int), st);
-    if (E > 0) fill_i32<<<1, 1, 0, st>>>(status, 1, 1);
+    if (E > 0 && N == 0) fill_i32<<<1, 1, 0, st>>>(status, 1, 1);
     return tagan_launch_status();
   }
-  const unsigned gN = ceil_div_i64(N, TB), gE = ceil_div_i64(E > 0 ? E : 1, TB);
-  const unsigned gW = ceil_div_i64((int64_t)N * 32, TB);
+  const unsigned gR = ceil_div_i64(R, TB), gE = ceil_div_i64(E > 0 ? E : 1, TB);
+  const unsigned gW = ceil_div_i64((int64_t)R * 32, TB);
   const unsigned gHeavy = 148 * 4;
 
-  fill_i32<<<gN, TB, 0, st>>>(cnt, 1, N);         // one self loop per row
-  fill_i32<<<gN, TB, 0, st>>>(cursor, 1, N);
-  if (E > 0) count_rows<<<gE, TB, 0, st>>>(edge_index, E, N, cnt, status);
-  exclusive_scan(cnt, off, N, scanws, st);
-  place_self_loops<<<gN, TB, 0, st>>>(off, bucket, N);
-  if (E > 0) scatter_edges<<<gE, TB, 0, st>>>(edge_index, E, N, off, cursor, bucket);
-  seg_sort_warp<true, false><<<gW, TB, 0, st>>>(off, bucket, nullptr, staged, nullptr, ucount, N);
-  seg_sort_block<true, false><<<gHeavy, TB, 0, st>>>(off, bucket, nullptr, staged, flags, ucount, N);
-  exclusive_scan(ucount, rowptr, N, scanws, st);
-  compact_rows<<<gW, TB, 0, st>>>(off, rowptr, staged, col, row, N);
+  fill_i32<<<gR, TB, 0, st>>>(cnt, 1, R);         // one self loop per local row
+  fill_i32<<<gR, TB, 0, st>>>(cursor, 1, R);
+  if (E > 0) count_rows<<<gE, TB, 0, st>>>(edge_index, E, N, row_begin, R, cnt, status);
+  exclusive_scan(cnt, off, R, scanws, st);
+  place_self_loops<<<gR, TB, 0, st>>>(off, bucket, R, row_begin);
+  if (E > 0) scatter_edges<<<gE, TB, 0, st>>>(edge_index, E, N, row_begin, R, off, cursor, bucket);
+  seg_sort_warp<true, false><<<gW, TB, 0, st>>>(off, bucket, nullptr, staged, nullptr, ucount, R);
+  seg_sort_block<true, false><<<gHeavy, TB, 0, st>>>(off, bucket, nullptr, staged, flags, ucount, R);
+  exclusive_scan(ucount, rowptr, R, scanws, st);
+  compact_rows<<<gW, TB, 0, st>>>(off, rowptr, staged, col, row, R);
 
-  if (transpose) {
-    const unsigned gT = ceil_div_i64(E + N, TB);
+  if (transpose) {                                 // indexed by GLOBAL source node, rows are local ids
+    const unsigned gN = ceil_div_i64(N, TB), gT = ceil_div_i64(E + R, TB);
+    const unsigned gWN = ceil_div_i64((int64_t)N * 32, TB);
     cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)N, st);
     cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)N, st);
-    count_cols<<<gT, TB, 0, st>>>(rowptr, col, N, cnt);
+    (void)gN;
+    count_cols<<<gT, TB, 0, st>>>(rowptr, col, R, cnt);
     exclusive_scan(cnt, rowptr_t, N, scanws, st);
-    scatter_cols<<<gT, TB, 0, st>>>(rowptr, col, row, N, rowptr_t, cursor, bucket, staged);
-    seg_sort_warp<false, true><<<gW, TB, 0, st>>>(rowptr_t, bucket, staged, row_t, perm_t, nullptr, N);
+    scatter_cols<<<gT, TB, 0, st>>>(rowptr, col, row, R, rowptr_t, cursor, bucket, staged);
+    seg_sort_warp<false, true><<<gWN, TB, 0, st>>>(rowptr_t, bucket, staged, row_t, perm_t, nullptr, N);
     seg_sort_block<false, true><<<gHeavy, TB, 0, st>>>(rowptr_t, bucket, staged, row_t, perm_t, nullptr, N);
   }
   return tagan_launch_status();
+}
+
+TAGAN_API int tagan_csr_build(const int64_t* edge_index, int64_t E, int32_t N, int32_t* rowptr, int32_t* col,
+                              int32_t* row, int32_t* rowptr_t, int32_t* row_t, int32_t* perm_t, int32_t* status,
+                              void* workspace, size_t workspace_bytes, tagan_stream_t stream) {
+  return tagan_csr_build_part(edge_index, E, N, 0, N, rowptr, col, row, rowptr_t, row_t, perm_t, status, workspace,
+                              workspace_bytes, stream);
 }

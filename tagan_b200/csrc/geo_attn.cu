@@ -129,7 +129,7 @@ __device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const float*
 
 template <int METRIC, int VEC, int NCHUNK>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-geo_attn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+geo_attn_fwd_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                     const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
                     const float* __restrict__ metric_param, float* __restrict__ ctx, float* __restrict__ lse,
                     float* __restrict__ attn) {
@@ -141,7 +141,7 @@ geo_attn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
   const int group = D / VEC;
   float q[NCHUNK][VEC], acc[NCHUNK][VEC], m[NCHUNK], l[NCHUNK], par[NCHUNK], qn[NCHUNK];
   int head[NCHUNK];
-  load_row<VEC, NCHUNK>(q, Q + (int64_t)row * ld, lane);
+  load_row<VEC, NCHUNK>(q, Q + (int64_t)row * ldq, lane);
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
     head[c] = (c * 32 * VEC + lane * VEC) / D;
@@ -217,7 +217,7 @@ geo_attn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
 // Row pass: dQ[i] = sum_e ds_e * dscore/dq, delta[i,h] = dctx_i . ctx_i, optional dparam partials.
 template <int METRIC, int VEC, int NCHUNK>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-geo_attn_bwd_row_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+geo_attn_bwd_row_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                         const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
                         const float* __restrict__ metric_param, const float* __restrict__ ctx,
                         const float* __restrict__ lse, const float* __restrict__ dctx, float* __restrict__ dQ,
@@ -230,7 +230,7 @@ geo_attn_bwd_row_kernel(const float* __restrict__ Q, const float* __restrict__ K
   const int group = D / VEC;
   float q[NCHUNK][VEC], go[NCHUNK][VEC], dq[NCHUNK][VEC], par[NCHUNK], qn[NCHUNK], ls[NCHUNK], dl[NCHUNK], dpar[NCHUNK];
   int head[NCHUNK];
-  load_row<VEC, NCHUNK>(q, Q + (int64_t)row * ld, lane);
+  load_row<VEC, NCHUNK>(q, Q + (int64_t)row * ldq, lane);
   load_row<VEC, NCHUNK>(go, dctx + (int64_t)row * H, lane);
   {
     float cx[NCHUNK][VEC];
@@ -303,7 +303,7 @@ geo_attn_bwd_row_kernel(const float* __restrict__ Q, const float* __restrict__ K
 // dK[j] = sum_e ds_e * dscore/dk.  Gathers Q[row], dctx[row], lse[row,h], delta[row,h].
 template <int METRIC, int VEC, int NCHUNK>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-geo_attn_bwd_col_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+geo_attn_bwd_col_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                         const int* __restrict__ rowptr_t, const int* __restrict__ row_t, int N, int heads, int D,
                         const float* __restrict__ metric_param, const float* __restrict__ lse,
                         const float* __restrict__ delta, const float* __restrict__ dctx, float* __restrict__ dK,
@@ -334,7 +334,7 @@ geo_attn_bwd_col_kernel(const float* __restrict__ Q, const float* __restrict__ K
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int r = __shfl_sync(FULL_MASK, myrow, min(j + u, n - 1));
-        load_row<VEC, NCHUNK>(qq[u], Q + (int64_t)r * ld, lane);
+        load_row<VEC, NCHUNK>(qq[u], Q + (int64_t)r * ldq, lane);
         load_row<VEC, NCHUNK>(gg[u], dctx + (int64_t)r * H, lane);
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
@@ -435,18 +435,62 @@ bool pick_shape(int H, int heads, Shape* s) {
 
 }  // namespace
 
+TAGAN_API int tagan_geo_attn_fwd_part(const float* Q, int64_t ldq, const float* K, const float* V, int64_t ldkv,
+                                      const int32_t* rowptr, const int32_t* col, int32_t n_rows, int32_t H,
+                                      int32_t heads, int32_t metric, const float* metric_param, float* ctx, float* lse,
+                                      float* attn, tagan_stream_t stream) {
+  if (!Q || !K || !V || !rowptr || !col || !ctx || !lse || n_rows < 0 || ldq < H || ldkv < H) return TAGAN_E_INVALID;
+  Shape sh;
+  if (!pick_shape(H, heads, &sh) || (ldq % sh.vec) || (ldkv % sh.vec)) return TAGAN_E_UNSUPPORTED;
+  if (n_rows == 0) return 0;
+  const int N = n_rows;
+  const int64_t ld = ldkv;
+  const int D = H / heads;
+  dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_METRIC(geo_attn_fwd_kernel, <<<grid, block, 0, st>>>(Q, ldq, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, attn))
+  return tagan_launch_status();
+}
+
 TAGAN_API int tagan_geo_attn_fwd(const float* Q, const float* K, const float* V, int64_t ld, const int32_t* rowptr,
                                  const int32_t* col, int32_t N, int32_t H, int32_t heads, int32_t metric,
                                  const float* metric_param, float* ctx, float* lse, float* attn,
                                  tagan_stream_t stream) {
-  if (!Q || !K || !V || !rowptr || !col || !ctx || !lse || N < 0 || ld < H) return TAGAN_E_INVALID;
+  return tagan_geo_attn_fwd_part(Q, ld, K, V, ld, rowptr, col, N, H, heads, metric, metric_param, ctx, lse, attn, stream);
+}
+
+TAGAN_API int tagan_geo_attn_bwd_part(const float* Q, int64_t ldq, const float* K, const float* V, int64_t ldkv,
+                                      const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
+                                      const int32_t* row_t, int32_t n_rows, int32_t n_src, int32_t H, int32_t heads,
+                                      int32_t metric, const float* metric_param, const float* ctx, const float* lse,
+                                      const float* dctx, float* dQ, int64_t lddq, float* dK, float* dV, int64_t lddkv,
+                                      float* delta_ws, float* dparam_ws, float* dparam, tagan_stream_t stream) {
+  if (!Q || !K || !V || !rowptr || !col || !rowptr_t || !row_t || !ctx || !lse || !dctx || !dQ || !dK || !dV ||
+      !delta_ws || n_rows < 0 || n_src < 0 || ldq < H || ldkv < H || lddq < H || lddkv < H)
+    return TAGAN_E_INVALID;
   Shape sh;
-  if (!pick_shape(H, heads, &sh) || (ld % sh.vec)) return TAGAN_E_UNSUPPORTED;
-  if (N == 0) return 0;
+  if (!pick_shape(H, heads, &sh) || (ldq % sh.vec) || (ldkv % sh.vec) || (lddq % sh.vec) || (lddkv % sh.vec))
+    return TAGAN_E_UNSUPPORTED;
+  const bool want_dparam = metric_param != nullptr && (metric == TAGAN_METRIC_GAUSSIAN || metric == TAGAN_METRIC_RBF);
+  if (want_dparam && (!dparam_ws || !dparam)) return TAGAN_E_INVALID;
   const int D = H / heads;
-  dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
+  const int64_t ld = ldkv;
   cudaStream_t st = as_stream(stream);
-  DISPATCH_METRIC(geo_attn_fwd_kernel, <<<grid, block, 0, st>>>(Q, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, attn))
+  float* dpr = want_dparam ? dparam_ws : nullptr;
+  dim3 block(WARPS_PER_BLOCK * 32);
+  if (n_rows > 0) {
+    const int N = n_rows;
+    const int64_t ldd = lddq;
+    dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    DISPATCH_METRIC(geo_attn_bwd_row_kernel, <<<grid, block, 0, st>>>(Q, ldq, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, dctx, dQ, ldd, delta_ws, dpr))
+  }
+  if (n_src > 0) {
+    const int N = n_src;
+    const int64_t ldd = lddkv;
+    dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    DISPATCH_METRIC(geo_attn_bwd_col_kernel, <<<grid, block, 0, st>>>(Q, ldq, K, V, ld, rowptr_t, row_t, N, heads, D, metric_param, lse, delta_ws, dctx, dK, dV, ldd))
+  }
+  if (want_dparam) reduce_rows_per_head<<<heads, 256, 0, st>>>(dparam_ws, n_rows, heads, dparam);
   return tagan_launch_status();
 }
 
@@ -456,20 +500,6 @@ TAGAN_API int tagan_geo_attn_bwd(const float* Q, const float* K, const float* V,
                                  const float* ctx, const float* lse, const float* dctx, float* dQ, float* dK,
                                  float* dV, int64_t ldd, float* delta_ws, float* dparam_ws, float* dparam,
                                  tagan_stream_t stream) {
-  if (!Q || !K || !V || !rowptr || !col || !rowptr_t || !row_t || !ctx || !lse || !dctx || !dQ || !dK || !dV ||
-      !delta_ws || N < 0 || ld < H || ldd < H)
-    return TAGAN_E_INVALID;
-  Shape sh;
-  if (!pick_shape(H, heads, &sh) || (ld % sh.vec) || (ldd % sh.vec)) return TAGAN_E_UNSUPPORTED;
-  const bool want_dparam = metric_param != nullptr && (metric == TAGAN_METRIC_GAUSSIAN || metric == TAGAN_METRIC_RBF);
-  if (want_dparam && (!dparam_ws || !dparam)) return TAGAN_E_INVALID;
-  if (N == 0) return 0;
-  const int D = H / heads;
-  dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
-  cudaStream_t st = as_stream(stream);
-  float* dpr = want_dparam ? dparam_ws : nullptr;
-  DISPATCH_METRIC(geo_attn_bwd_row_kernel, <<<grid, block, 0, st>>>(Q, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, dctx, dQ, ldd, delta_ws, dpr))
-  DISPATCH_METRIC(geo_attn_bwd_col_kernel, <<<grid, block, 0, st>>>(Q, K, V, ld, rowptr_t, row_t, N, heads, D, metric_param, lse, delta_ws, dctx, dK, dV, ldd))
-  if (want_dparam) reduce_rows_per_head<<<heads, 256, 0, st>>>(dparam_ws, N, heads, dparam);
-  return tagan_launch_status();
+  return tagan_geo_attn_bwd_part(Q, ld, K, V, ld, rowptr, col, rowptr_t, row_t, N, N, H, heads, metric, metric_param,
+                                 ctx, lse, dctx, dQ, ldd, dK, dV, ldd, delta_ws, dparam_ws, dparam, stream);
 }

@@ -1,0 +1,137 @@
+"""Node-partitioned geometric attention for one large graph.
+
+Rank r owns the contiguous node range ``NodePartition.bounds(r)``: its query rows, its slice of the
+features and of every per-node temporal stage (those need no communication).  The geometric layer needs
+the projected K|V rows of remote neighbours:
+
+    forward : K|V_local [n_loc,2H]  --all_gather-->  K|V_global [N,2H]  -> fused kernel over local rows
+    backward: column pass over ALL source nodes gives partial dK|dV [N,2H]  --reduce_scatter(sum)-->  local
+
+On a uniform random graph ~(world-1)/world of the neighbours are remote, so the halo is the whole K|V
+matrix and a plain all-gather is the right collective (NVSwitch: every peer at full bandwidth).
+``comm`` abstracts the two collectives so the same code runs under torch.distributed (NCCL) and under the
+single-process emulation used by the 1-GPU tests.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .dist import NodePartition
+from .ops import CALLS, CSR, _f32c, _ptr, _stream, workspace
+
+
+def build_csr_part(edge_index: torch.Tensor, part: NodePartition, rank: int, transpose: bool = True) -> CSR:
+    """CSR of this rank's rows (local ids) against global columns, built on device from the FULL edge list."""
+    lib = _lib.load()
+    ei = edge_index.long().contiguous()
+    e = ei.shape[1]
+    n = part.num_nodes
+    lo, hi = part.bounds(rank)
+    r = hi - lo
+    dev = ei.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    cap = e + r
+    rowptr = torch.empty(r + 1, **i32)
+    col = torch.empty(max(cap, 1), **i32)
+    row = torch.empty(max(cap, 1), **i32)
+    status = torch.empty(1, **i32)
+    rowptr_t = row_t = perm_t = None
+    if transpose:
+        rowptr_t = torch.empty(n + 1, **i32)
+        row_t = torch.empty(max(cap, 1), **i32)
+        perm_t = torch.empty(max(cap, 1), **i32)
+    ws = workspace(lib.tagan_csr_workspace_bytes(e, n), dev)
+    rc = lib.tagan_csr_build_part(_ptr(ei) if e else None, e, n, lo, r, _ptr(rowptr), _ptr(col), _ptr(row),
+                                  _ptr(rowptr_t), _ptr(row_t), _ptr(perm_t), _ptr(status), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "tagan_csr_build_part")
+    CALLS["n"] += 22 if transpose else 12
+    return CSR(r, e, rowptr, col, row, rowptr_t, row_t, perm_t, status)
+
+
+class TorchDistComm:
+    """all_gather / reduce_scatter of equal-size blocks over a torch.distributed group (NCCL)."""
+
+    def __init__(self, part: NodePartition, rank: int, group=None):
+        self.part, self.rank, self.group = part, rank, group
+        assert part.num_nodes % part.world == 0, "equal blocks required (pad the graph to a multiple of world)"
+
+    def all_gather_rows(self, local: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.part.num_nodes, local.shape[1], dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out
+
+    def reduce_scatter_rows(self, full: torch.Tensor) -> torch.Tensor:
+        n_loc = self.part.num_nodes // self.part.world
+        out = torch.empty(n_loc, full.shape[1], dtype=full.dtype, device=full.device)
+        dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group)
+        return out
+
+
+class _PartGeoAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv_loc, metric_param, csr: CSR, comm, heads: int, metric: int, n_src: int):
+        lib = _lib.load()
+        qkv2 = _f32c(qkv_loc).contiguous()
+        n_loc, three_h = qkv2.shape
+        h = three_h // 3
+        kv = comm.all_gather_rows(qkv2[:, h:])                       # [N, 2H]  (the halo exchange)
+        ctxv = torch.empty(n_loc, h, dtype=torch.float32, device=qkv2.device)
+        lse = torch.empty(n_loc, heads, dtype=torch.float32, device=qkv2.device)
+        k_ptr, v_ptr = C.c_void_p(kv.data_ptr()), C.c_void_p(kv.data_ptr() + h * 4)
+        rc = lib.tagan_geo_attn_fwd_part(_ptr(qkv2), three_h, k_ptr, v_ptr, 2 * h, _ptr(csr.rowptr), _ptr(csr.col), n_loc,
+                                         h, heads, metric, _ptr(metric_param), _ptr(ctxv), _ptr(lse), None, _stream())
+        _lib.check(rc, "tagan_geo_attn_fwd_part")
+        CALLS["n"] += 1
+        ctx.save_for_backward(qkv2, kv, metric_param, ctxv, lse)
+        ctx.csr, ctx.comm, ctx.heads, ctx.metric, ctx.n_src = csr, comm, heads, metric, n_src
+        return ctxv
+
+    @staticmethod
+    def backward(ctx, dctx):
+        lib = _lib.load()
+        qkv2, kv, metric_param, ctxv, lse = ctx.saved_tensors
+        csr, comm, heads, metric, n_src = ctx.csr, ctx.comm, ctx.heads, ctx.metric, ctx.n_src
+        n_loc, three_h = qkv2.shape
+        h = three_h // 3
+        dev = qkv2.device
+        dctx = _f32c(dctx).contiguous()
+        dqkv = torch.empty(n_loc, three_h, dtype=torch.float32, device=dev)
+        dkv_part = torch.empty(n_src, 2 * h, dtype=torch.float32, device=dev)
+        delta = torch.empty(n_loc, heads, dtype=torch.float32, device=dev)
+        want_dp = metric_param is not None and metric in (7, 8)
+        dp_ws = torch.empty(n_loc, heads, dtype=torch.float32, device=dev) if want_dp else None
+        dparam = torch.empty(heads, dtype=torch.float32, device=dev) if want_dp else None
+        k_ptr, v_ptr = C.c_void_p(kv.data_ptr()), C.c_void_p(kv.data_ptr() + h * 4)
+        dk_ptr, dv_ptr = C.c_void_p(dkv_part.data_ptr()), C.c_void_p(dkv_part.data_ptr() + h * 4)
+        rc = lib.tagan_geo_attn_bwd_part(_ptr(qkv2), three_h, k_ptr, v_ptr, 2 * h, _ptr(csr.rowptr), _ptr(csr.col),
+                                         _ptr(csr.rowptr_t), _ptr(csr.row_t), n_loc, n_src, h, heads, metric,
+                                         _ptr(metric_param), _ptr(ctxv), _ptr(lse), _ptr(dctx), _ptr(dqkv), three_h,
+                                         dk_ptr, dv_ptr, 2 * h, _ptr(delta), _ptr(dp_ws), _ptr(dparam), _stream())
+        _lib.check(rc, "tagan_geo_attn_bwd_part")
+        CALLS["n"] += 2
+        dqkv[:, h:] = comm.reduce_scatter_rows(dkv_part)             # sum of every rank's partial dK|dV
+        return dqkv, dparam, None, None, None, None, None
+
+
+def geo_attention_core_part(qkv_loc, csr: CSR, comm, heads: int, metric: str, n_src: int, metric_param=None):
+    return _PartGeoAttnFn.apply(qkv_loc, metric_param, csr, comm, heads, ops.METRIC_ID[metric], n_src)
+
+
+def geometric_layer_part(layer, x_loc: torch.Tensor, csr: CSR, comm, n_src: int) -> torch.Tensor:
+    """``GeometricAttention.forward`` (reference geometric_attention.py:518-598) on this rank's node slice.
+    ``layer`` is a ``tagan_b200.GeometricAttention`` with replicated weights."""
+    ln = layer.use_layer_norm
+    xn = ops.layer_norm(x_loc, layer.layer_norm1.weight, layer.layer_norm1.bias) if ln else x_loc
+    w_qkv = torch.cat([layer.q_linear.weight, layer.k_linear.weight, layer.v_linear.weight], 0)
+    b_qkv = torch.cat([layer.q_linear.bias, layer.k_linear.bias, layer.v_linear.bias], 0)
+    qkv = ops.linear(xn, w_qkv, b_qkv)
+    ctxv = geo_attention_core_part(qkv, csr, comm, layer.num_heads, layer.distance_metric, n_src,
+                                   getattr(layer, "distance_param", None))
+    o = ops.linear(ctxv, layer.output_proj.weight, layer.output_proj.bias)
+    if ln:
+        return ops.layer_norm(o, layer.layer_norm2.weight, layer.layer_norm2.bias, res=x_loc)
+    return ops.add(o, x_loc)
