@@ -127,37 +127,74 @@ __device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const float*
   for (int c = 0; c < NCHUNK; ++c) VecIO<VEC>::load(dst[c], base + c * 32 * VEC + lane * VEC);
 }
 
+// Rows (or, in the column pass, source nodes) with more than HEAVY_THRESH entries are "heavy": the
+// warp-per-row kernels skip them and a second launch gives each of them a whole CTA -- its 8 warps take
+// contiguous slices of the entries and their partial states are merged through shared memory in warp
+// order, so the result stays deterministic and independent of scheduling (power-law graphs, config 2).
+constexpr int HEAVY_THRESH = 128;
+constexpr int HEAVY_GRID = 148 * 2;
+
+// Calls f(row) with the whole CTA for every row whose entry count exceeds HEAVY_THRESH.
+template <typename F>
+__device__ __forceinline__ void for_each_heavy_row(const int* __restrict__ ptr, int N, F f) {
+  __shared__ int heavy_list[WARPS_PER_BLOCK * 32];
+  __shared__ int heavy_count;
+  for (int base = blockIdx.x * (WARPS_PER_BLOCK * 32); base < N; base += gridDim.x * (WARPS_PER_BLOCK * 32)) {
+    if (threadIdx.x == 0) heavy_count = 0;
+    __syncthreads();
+    const int r = base + threadIdx.x;
+    if (r < N && ptr[r + 1] - ptr[r] > HEAVY_THRESH) heavy_list[atomicAdd(&heavy_count, 1)] = r;
+    __syncthreads();
+    const int cnt = heavy_count;
+    for (int i = 0; i < cnt; ++i) {
+      f(heavy_list[i]);
+      __syncthreads();
+    }
+  }
+}
+
+// slice of [beg,end) owned by warp w of WARPS_PER_BLOCK (multiples of 32 entries so index loads stay aligned)
+__device__ __forceinline__ void warp_slice(int beg, int end, int w, int& b, int& e) {
+  int per = (end - beg + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  per = (per + 31) & ~31;
+  b = min(end, beg + w * per);
+  e = min(end, b + per);
+}
+
 template <int METRIC, int VEC, int NCHUNK>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-geo_attn_fwd_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
-                    const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
-                    const float* __restrict__ metric_param, float* __restrict__ ctx, float* __restrict__ lse,
-                    float* __restrict__ attn) {
-  constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
-  constexpr int H = 32 * VEC * NCHUNK;
-  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= N) return;
-  const int group = D / VEC;
-  float q[NCHUNK][VEC], acc[NCHUNK][VEC], m[NCHUNK], l[NCHUNK], par[NCHUNK], qn[NCHUNK];
+struct RowCtx {
+  float q[NCHUNK][VEC], par[NCHUNK], qn[NCHUNK];
   int head[NCHUNK];
-  load_row<VEC, NCHUNK>(q, Q + (int64_t)row * ldq, lane);
+  int group;
+};
+
+template <int METRIC, int VEC, int NCHUNK>
+__device__ __forceinline__ void init_row(RowCtx<METRIC, VEC, NCHUNK>& rc, const float* qrow, const float* metric_param,
+                                         int D, int lane) {
+  rc.group = D / VEC;
+  load_row<VEC, NCHUNK>(rc.q, qrow, lane);
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
-    head[c] = (c * 32 * VEC + lane * VEC) / D;
-    par[c] = head_param<METRIC>(metric_param, head[c], D);
-    m[c] = -INFINITY; l[c] = 0.f; qn[c] = 0.f;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[c][i] = 0.f;
+    rc.head[c] = (c * 32 * VEC + lane * VEC) / D;
+    rc.par[c] = head_param<METRIC>(metric_param, rc.head[c], D);
+    rc.qn[c] = 0.f;
     if (MetricTraits<METRIC>::kCos) {
       float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) t = fmaf(q[c][i], q[c][i], t);
-      t = sqrtf(group_sum(t, group));
-      qn[c] = t == 0.f ? 1e-8f : t;
+      for (int i = 0; i < VEC; ++i) t = fmaf(rc.q[c][i], rc.q[c][i], t);
+      t = sqrtf(group_sum(t, rc.group));
+      rc.qn[c] = t == 0.f ? 1e-8f : t;
     }
   }
-  const int beg = rowptr[row], end = rowptr[row + 1];
+}
+
+// online-softmax walk over entries [beg,end) of one row
+template <int METRIC, int VEC, int NCHUNK>
+__device__ __forceinline__ void fwd_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float* __restrict__ K,
+                                         const float* __restrict__ V, int64_t ld, const int* __restrict__ col, int beg,
+                                         int end, int lane, float (&m)[NCHUNK], float (&l)[NCHUNK],
+                                         float (&acc)[NCHUNK][VEC]) {
+  constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
   for (int base = beg; base < end; base += 32) {
     const int n = min(32, end - base);
     const int mycol = lane < n ? __ldg(col + base + lane) : 0;
@@ -175,7 +212,7 @@ geo_attn_fwd_kernel(const float* __restrict__ Q, int64_t ldq, const float* __res
 #pragma unroll
           for (int c = 0; c < NCHUNK; ++c) {
             float p1, p2;
-            const float s = score_from_vectors<METRIC, VEC>(q[c], kk[u][c], group, par[c], qn[c], p1, p2);
+            const float s = score_from_vectors<METRIC, VEC>(rc.q[c], kk[u][c], rc.group, rc.par[c], rc.qn[c], p1, p2);
             const float mn = fmaxf(m[c], s);
             const float sc = expf(m[c] - mn);
             const float p = expf(s - mn);
@@ -188,79 +225,128 @@ geo_attn_fwd_kernel(const float* __restrict__ Q, int64_t ldq, const float* __res
       }
     }
   }
-  float lse_c[NCHUNK];
+}
+
+template <int METRIC, int VEC, int NCHUNK>
+__device__ __forceinline__ void fwd_attn_pass(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float* __restrict__ K,
+                                              int64_t ld, const int* __restrict__ col, int beg, int end, int lane,
+                                              int heads, const float (&lse_c)[NCHUNK], float* __restrict__ attn) {
+  for (int e = beg; e < end; ++e) {
+    const int cj = __ldg(col + e);
+    float kr[NCHUNK][VEC];
+    load_row<VEC, NCHUNK>(kr, K + (int64_t)cj * ld, lane);
 #pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) {
-    const float inv = 1.f / l[c];
-    float o[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = acc[c][i] * inv;
-    VecIO<VEC>::store(ctx + (int64_t)row * H + c * 32 * VEC + lane * VEC, o);
-    lse_c[c] = m[c] + logf(l[c]);
-    if ((lane & (group - 1)) == 0) lse[(int64_t)row * heads + head[c]] = lse_c[c];   // group leader
-  }
-  if (attn != nullptr) {   // optional second pass: per-entry softmax weights
-    for (int e = beg; e < end; ++e) {
-      const int cj = __ldg(col + e);
-      float kr[NCHUNK][VEC];
-      load_row<VEC, NCHUNK>(kr, K + (int64_t)cj * ld, lane);
-#pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        float p1, p2;
-        const float s = score_from_vectors<METRIC, VEC>(q[c], kr[c], group, par[c], qn[c], p1, p2);
-        if ((lane & (group - 1)) == 0) attn[(int64_t)e * heads + head[c]] = expf(s - lse_c[c]);
-      }
+    for (int c = 0; c < NCHUNK; ++c) {
+      float p1, p2;
+      const float s = score_from_vectors<METRIC, VEC>(rc.q[c], kr[c], rc.group, rc.par[c], rc.qn[c], p1, p2);
+      if ((lane & (rc.group - 1)) == 0) attn[(int64_t)e * heads + rc.head[c]] = expf(s - lse_c[c]);
     }
   }
 }
 
-// Row pass: dQ[i] = sum_e ds_e * dscore/dq, delta[i,h] = dctx_i . ctx_i, optional dparam partials.
-template <int METRIC, int VEC, int NCHUNK>
+template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-geo_attn_bwd_row_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
-                        const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
-                        const float* __restrict__ metric_param, const float* __restrict__ ctx,
-                        const float* __restrict__ lse, const float* __restrict__ dctx, float* __restrict__ dQ,
-                        int64_t ldd, float* __restrict__ delta, float* __restrict__ dparam_rows) {
-  constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
+geo_attn_fwd_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+                    const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
+                    const float* __restrict__ metric_param, float* __restrict__ ctx, float* __restrict__ lse,
+                    float* __restrict__ attn) {
   constexpr int H = 32 * VEC * NCHUNK;
-  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= N) return;
-  const int group = D / VEC;
-  float q[NCHUNK][VEC], go[NCHUNK][VEC], dq[NCHUNK][VEC], par[NCHUNK], qn[NCHUNK], ls[NCHUNK], dl[NCHUNK], dpar[NCHUNK];
-  int head[NCHUNK];
-  load_row<VEC, NCHUNK>(q, Q + (int64_t)row * ldq, lane);
-  load_row<VEC, NCHUNK>(go, dctx + (int64_t)row * H, lane);
-  {
-    float cx[NCHUNK][VEC];
-    load_row<VEC, NCHUNK>(cx, ctx + (int64_t)row * H, lane);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto finish = [&](const RowCtx<METRIC, VEC, NCHUNK>& rc, int row, const float (&m)[NCHUNK], const float (&l)[NCHUNK],
+                    const float (&acc)[NCHUNK][VEC], float (&lse_c)[NCHUNK]) {
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
-      float t = 0.f;
+      const float inv = 1.f / l[c];
+      float o[VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) t = fmaf(go[c][i], cx[c][i], t);
-      dl[c] = group_sum(t, group);
+      for (int i = 0; i < VEC; ++i) o[i] = acc[c][i] * inv;
+      VecIO<VEC>::store(ctx + (int64_t)row * H + c * 32 * VEC + lane * VEC, o);
+      lse_c[c] = m[c] + logf(l[c]);
+      if ((lane & (rc.group - 1)) == 0) lse[(int64_t)row * heads + rc.head[c]] = lse_c[c];   // group leader
     }
-  }
+  };
+  if (!HEAVY) {
+    const int row = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (row >= N) return;
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    if (end - beg > HEAVY_THRESH) return;
+    RowCtx<METRIC, VEC, NCHUNK> rc;
+    init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane);
+    float m[NCHUNK], l[NCHUNK], acc[NCHUNK][VEC], lse_c[NCHUNK];
 #pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) {
-    head[c] = (c * 32 * VEC + lane * VEC) / D;
-    par[c] = head_param<METRIC>(metric_param, head[c], D);
-    ls[c] = __ldg(lse + (int64_t)row * heads + head[c]);
-    dpar[c] = 0.f; qn[c] = 0.f;
+    for (int c = 0; c < NCHUNK; ++c) {
+      m[c] = -INFINITY; l[c] = 0.f;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) dq[c][i] = 0.f;
-    if (MetricTraits<METRIC>::kCos) {
-      float t = 0.f;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) t = fmaf(q[c][i], q[c][i], t);
-      t = sqrtf(group_sum(t, group));
-      qn[c] = t == 0.f ? 1e-8f : t;
+      for (int i = 0; i < VEC; ++i) acc[c][i] = 0.f;
     }
-    if ((lane & (group - 1)) == 0) delta[(int64_t)row * heads + head[c]] = dl[c];
+    fwd_walk<METRIC, VEC, NCHUNK>(rc, K, V, ld, col, beg, end, lane, m, l, acc);
+    finish(rc, row, m, l, acc, lse_c);
+    if (attn != nullptr) fwd_attn_pass<METRIC, VEC, NCHUNK>(rc, K, ld, col, beg, end, lane, heads, lse_c, attn);
+  } else {
+    __shared__ float sm_m[WARPS_PER_BLOCK][NCHUNK][32], sm_l[WARPS_PER_BLOCK][NCHUNK][32];
+    __shared__ float sm_acc[WARPS_PER_BLOCK][NCHUNK][VEC][32];
+    __shared__ float sm_lse[NCHUNK][32];
+    for_each_heavy_row(rowptr, N, [&](int row) {
+      const int beg = rowptr[row], end = rowptr[row + 1];
+      int b, e;
+      warp_slice(beg, end, w, b, e);
+      RowCtx<METRIC, VEC, NCHUNK> rc;
+      init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane);
+      float m[NCHUNK], l[NCHUNK], acc[NCHUNK][VEC], lse_c[NCHUNK];
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        m[c] = -INFINITY; l[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[c][i] = 0.f;
+      }
+      fwd_walk<METRIC, VEC, NCHUNK>(rc, K, V, ld, col, b, e, lane, m, l, acc);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        sm_m[w][c][lane] = m[c]; sm_l[w][c][lane] = l[c];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sm_acc[w][c][i][lane] = acc[c][i];
+      }
+      __syncthreads();
+      if (w == 0) {            // merge the 8 partial softmax states in warp order
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          float M = sm_m[0][c][lane];
+          for (int k = 1; k < WARPS_PER_BLOCK; ++k) M = fmaxf(M, sm_m[k][c][lane]);
+          float L = 0.f, A[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) A[i] = 0.f;
+          for (int k = 0; k < WARPS_PER_BLOCK; ++k) {
+            const float sc = expf(sm_m[k][c][lane] - M);      // exp(-inf) = 0 for empty slices
+            L = fmaf(sm_l[k][c][lane], sc, L);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) A[i] = fmaf(sm_acc[k][c][i][lane], sc, A[i]);
+          }
+          m[c] = M; l[c] = L;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[c][i] = A[i];
+        }
+        finish(rc, row, m, l, acc, lse_c);
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) sm_lse[c][lane] = lse_c[c];
+      }
+      if (attn != nullptr) {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) lse_c[c] = sm_lse[c][lane];
+        fwd_attn_pass<METRIC, VEC, NCHUNK>(rc, K, ld, col, b, e, lane, heads, lse_c, attn);
+      }
+    });
   }
-  const int beg = rowptr[row], end = rowptr[row + 1];
+}
+
+// ---- row pass: dQ[i] = sum_e ds_e * dscore/dq, delta[i,h] = dctx_i . ctx_i, optional dparam partials.
+template <int METRIC, int VEC, int NCHUNK>
+__device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float (&go)[NCHUNK][VEC],
+                                             const float (&ls)[NCHUNK], const float (&dl)[NCHUNK],
+                                             const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+                                             const int* __restrict__ col, int beg, int end, int lane,
+                                             float (&dq)[NCHUNK][VEC], float (&dpar)[NCHUNK]) {
+  constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
   for (int base = beg; base < end; base += 32) {
     const int n = min(32, end - base);
     const int mycol = lane < n ? __ldg(col + base + lane) : 0;
@@ -278,54 +364,124 @@ geo_attn_bwd_row_kernel(const float* __restrict__ Q, int64_t ldq, const float* _
 #pragma unroll
           for (int c = 0; c < NCHUNK; ++c) {
             float p1, p2;
-            const float s = score_from_vectors<METRIC, VEC>(q[c], kk[u][c], group, par[c], qn[c], p1, p2);
+            const float s = score_from_vectors<METRIC, VEC>(rc.q[c], kk[u][c], rc.group, rc.par[c], rc.qn[c], p1, p2);
             const float a = expf(s - ls[c]);
             float dp = 0.f;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) dp = fmaf(go[c][i], vv[u][c][i], dp);
-            dp = group_sum(dp, group);
+            dp = group_sum(dp, rc.group);
             const float ds = a * (dp - dl[c]);
-            dpar[c] += accum_score_grad<METRIC, VEC, true>(ds, q[c], kk[u][c], s, p1, p2, par[c], qn[c], dq[c]);
+            dpar[c] += accum_score_grad<METRIC, VEC, true>(ds, rc.q[c], kk[u][c], s, p1, p2, rc.par[c], rc.qn[c], dq[c]);
           }
         }
       }
     }
   }
+}
+
+template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+geo_attn_bwd_row_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+                        const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
+                        const float* __restrict__ metric_param, const float* __restrict__ ctx,
+                        const float* __restrict__ lse, const float* __restrict__ dctx, float* __restrict__ dQ,
+                        int64_t ldd, float* __restrict__ delta, float* __restrict__ dparam_rows) {
+  constexpr int H = 32 * VEC * NCHUNK;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-row prologue shared by both modes: q, dctx row, lse, delta = dctx . ctx
+  auto prologue = [&](int row, RowCtx<METRIC, VEC, NCHUNK>& rc, float (&go)[NCHUNK][VEC], float (&ls)[NCHUNK],
+                      float (&dl)[NCHUNK], bool write_delta) {
+    init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane);
+    load_row<VEC, NCHUNK>(go, dctx + (int64_t)row * H, lane);
+    float cx[NCHUNK][VEC];
+    load_row<VEC, NCHUNK>(cx, ctx + (int64_t)row * H, lane);
 #pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) {
-    VecIO<VEC>::store(dQ + (int64_t)row * ldd + c * 32 * VEC + lane * VEC, dq[c]);
-    if (MetricTraits<METRIC>::kParam && dparam_rows != nullptr && (lane & (group - 1)) == 0)
-      dparam_rows[(int64_t)row * heads + head[c]] = dpar[c];
+    for (int c = 0; c < NCHUNK; ++c) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) t = fmaf(go[c][i], cx[c][i], t);
+      dl[c] = group_sum(t, rc.group);
+      ls[c] = __ldg(lse + (int64_t)row * heads + rc.head[c]);
+      if (write_delta && (lane & (rc.group - 1)) == 0) delta[(int64_t)row * heads + rc.head[c]] = dl[c];
+    }
+  };
+  auto store = [&](const RowCtx<METRIC, VEC, NCHUNK>& rc, int row, const float (&dq)[NCHUNK][VEC], const float (&dpar)[NCHUNK]) {
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      VecIO<VEC>::store(dQ + (int64_t)row * ldd + c * 32 * VEC + lane * VEC, dq[c]);
+      if (MetricTraits<METRIC>::kParam && dparam_rows != nullptr && (lane & (rc.group - 1)) == 0)
+        dparam_rows[(int64_t)row * heads + rc.head[c]] = dpar[c];
+    }
+  };
+  if (!HEAVY) {
+    const int row = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (row >= N) return;
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    if (end - beg > HEAVY_THRESH) return;
+    RowCtx<METRIC, VEC, NCHUNK> rc;
+    float go[NCHUNK][VEC], ls[NCHUNK], dl[NCHUNK], dq[NCHUNK][VEC], dpar[NCHUNK];
+    prologue(row, rc, go, ls, dl, true);
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      dpar[c] = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) dq[c][i] = 0.f;
+    }
+    bwd_row_walk<METRIC, VEC, NCHUNK>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar);
+    store(rc, row, dq, dpar);
+  } else {
+    __shared__ float sm_dq[WARPS_PER_BLOCK][NCHUNK][VEC][32];
+    __shared__ float sm_dp[WARPS_PER_BLOCK][NCHUNK][32];
+    for_each_heavy_row(rowptr, N, [&](int row) {
+      const int beg = rowptr[row], end = rowptr[row + 1];
+      int b, e;
+      warp_slice(beg, end, w, b, e);
+      RowCtx<METRIC, VEC, NCHUNK> rc;
+      float go[NCHUNK][VEC], ls[NCHUNK], dl[NCHUNK], dq[NCHUNK][VEC], dpar[NCHUNK];
+      prologue(row, rc, go, ls, dl, w == 0);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        dpar[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dq[c][i] = 0.f;
+      }
+      bwd_row_walk<METRIC, VEC, NCHUNK>(rc, go, ls, dl, K, V, ld, col, b, e, lane, dq, dpar);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        sm_dp[w][c][lane] = dpar[c];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sm_dq[w][c][i][lane] = dq[c][i];
+      }
+      __syncthreads();
+      if (w == 0) {
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          dpar[c] = sm_dp[0][c][lane];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) dq[c][i] = sm_dq[0][c][i][lane];
+          for (int k = 1; k < WARPS_PER_BLOCK; ++k) {
+            dpar[c] += sm_dp[k][c][lane];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dq[c][i] += sm_dq[k][c][i][lane];
+          }
+        }
+        store(rc, row, dq, dpar);
+      }
+    });
   }
 }
 
-// Column pass over the transposed CSR: for source node j, dV[j] = sum_e a_e dctx[row_e],
+// ---- column pass over the transposed CSR: for source node j, dV[j] = sum_e a_e dctx[row_e],
 // dK[j] = sum_e ds_e * dscore/dk.  Gathers Q[row], dctx[row], lse[row,h], delta[row,h].
 template <int METRIC, int VEC, int NCHUNK>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-geo_attn_bwd_col_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
-                        const int* __restrict__ rowptr_t, const int* __restrict__ row_t, int N, int heads, int D,
-                        const float* __restrict__ metric_param, const float* __restrict__ lse,
-                        const float* __restrict__ delta, const float* __restrict__ dctx, float* __restrict__ dK,
-                        float* __restrict__ dV, int64_t ldd) {
+__device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], const float (&v)[NCHUNK][VEC],
+                                             const float (&par)[NCHUNK], const int (&head)[NCHUNK], int group,
+                                             const float* __restrict__ Q, int64_t ldq, const float* __restrict__ dctx,
+                                             const float* __restrict__ lse, const float* __restrict__ delta, int heads,
+                                             const int* __restrict__ row_t, int beg, int end, int lane,
+                                             float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC]) {
   constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
   constexpr int H = 32 * VEC * NCHUNK;
-  const int node = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (node >= N) return;
-  const int group = D / VEC;
-  float k[NCHUNK][VEC], v[NCHUNK][VEC], dk[NCHUNK][VEC], dv[NCHUNK][VEC], par[NCHUNK];
-  int head[NCHUNK];
-  load_row<VEC, NCHUNK>(k, K + (int64_t)node * ld, lane);
-  load_row<VEC, NCHUNK>(v, V + (int64_t)node * ld, lane);
-#pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) {
-    head[c] = (c * 32 * VEC + lane * VEC) / D;
-    par[c] = head_param<METRIC>(metric_param, head[c], D);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { dk[c][i] = 0.f; dv[c][i] = 0.f; }
-  }
-  const int beg = rowptr_t[node], end = rowptr_t[node + 1];
   for (int base = beg; base < end; base += 32) {
     const int n = min(32, end - base);
     const int myrow = lane < n ? __ldg(row_t + base + lane) : 0;
@@ -372,10 +528,73 @@ geo_attn_bwd_col_kernel(const float* __restrict__ Q, int64_t ldq, const float* _
       }
     }
   }
+}
+
+template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+geo_attn_bwd_col_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+                        const int* __restrict__ rowptr_t, const int* __restrict__ row_t, int N, int heads, int D,
+                        const float* __restrict__ metric_param, const float* __restrict__ lse,
+                        const float* __restrict__ delta, const float* __restrict__ dctx, float* __restrict__ dK,
+                        float* __restrict__ dV, int64_t ldd) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = D / VEC;
+  auto load_node = [&](int node, float (&k)[NCHUNK][VEC], float (&v)[NCHUNK][VEC], float (&par)[NCHUNK], int (&head)[NCHUNK],
+                       float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC]) {
+    load_row<VEC, NCHUNK>(k, K + (int64_t)node * ld, lane);
+    load_row<VEC, NCHUNK>(v, V + (int64_t)node * ld, lane);
 #pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) {
-    VecIO<VEC>::store(dK + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dk[c]);
-    VecIO<VEC>::store(dV + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dv[c]);
+    for (int c = 0; c < NCHUNK; ++c) {
+      head[c] = (c * 32 * VEC + lane * VEC) / D;
+      par[c] = head_param<METRIC>(metric_param, head[c], D);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { dk[c][i] = 0.f; dv[c][i] = 0.f; }
+    }
+  };
+  auto store = [&](int node, const float (&dk)[NCHUNK][VEC], const float (&dv)[NCHUNK][VEC]) {
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      VecIO<VEC>::store(dK + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dk[c]);
+      VecIO<VEC>::store(dV + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dv[c]);
+    }
+  };
+  if (!HEAVY) {
+    const int node = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (node >= N) return;
+    const int beg = rowptr_t[node], end = rowptr_t[node + 1];
+    if (end - beg > HEAVY_THRESH) return;
+    float k[NCHUNK][VEC], v[NCHUNK][VEC], dk[NCHUNK][VEC], dv[NCHUNK][VEC], par[NCHUNK];
+    int head[NCHUNK];
+    load_node(node, k, v, par, head, dk, dv);
+    bwd_col_walk<METRIC, VEC, NCHUNK>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv);
+    store(node, dk, dv);
+  } else {
+    __shared__ float sm_dk[WARPS_PER_BLOCK][NCHUNK][VEC][32], sm_dv[WARPS_PER_BLOCK][NCHUNK][VEC][32];
+    for_each_heavy_row(rowptr_t, N, [&](int node) {
+      const int beg = rowptr_t[node], end = rowptr_t[node + 1];
+      int b, e;
+      warp_slice(beg, end, w, b, e);
+      float k[NCHUNK][VEC], v[NCHUNK][VEC], dk[NCHUNK][VEC], dv[NCHUNK][VEC], par[NCHUNK];
+      int head[NCHUNK];
+      load_node(node, k, v, par, head, dk, dv);
+      bwd_col_walk<METRIC, VEC, NCHUNK>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, b, e, lane, dk, dv);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { sm_dk[w][c][i][lane] = dk[c][i]; sm_dv[w][c][i][lane] = dv[c][i]; }
+      __syncthreads();
+      if (w == 0) {
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            float a = sm_dk[0][c][i][lane], bb = sm_dv[0][c][i][lane];
+            for (int kk = 1; kk < WARPS_PER_BLOCK; ++kk) { a += sm_dk[kk][c][i][lane]; bb += sm_dv[kk][c][i][lane]; }
+            dk[c][i] = a; dv[c][i] = bb;
+          }
+        store(node, dk, dv);
+      }
+    });
   }
 }
 
@@ -412,13 +631,16 @@ bool pick_shape(int H, int heads, Shape* s) {
   return true;
 }
 
-#define DISPATCH_SHAPE(METRIC, FN, ...)                                          \
-  if (sh.vec == 1 && sh.nchunk == 1) FN<METRIC, 1, 1> __VA_ARGS__;                \
-  else if (sh.vec == 2 && sh.nchunk == 1) FN<METRIC, 2, 1> __VA_ARGS__;           \
-  else if (sh.vec == 4 && sh.nchunk == 1) FN<METRIC, 4, 1> __VA_ARGS__;           \
-  else if (sh.vec == 4 && sh.nchunk == 2) FN<METRIC, 4, 2> __VA_ARGS__;           \
-  else FN<METRIC, 4, 4> __VA_ARGS__;
+#define DISPATCH_SHAPE(METRIC, FN, ...)                                                     \
+  if (sh.vec == 1 && sh.nchunk == 1) { FN<METRIC, 1, 1, false> GRID_L __VA_ARGS__; FN<METRIC, 1, 1, true> GRID_H __VA_ARGS__; }      \
+  else if (sh.vec == 2 && sh.nchunk == 1) { FN<METRIC, 2, 1, false> GRID_L __VA_ARGS__; FN<METRIC, 2, 1, true> GRID_H __VA_ARGS__; } \
+  else if (sh.vec == 4 && sh.nchunk == 1) { FN<METRIC, 4, 1, false> GRID_L __VA_ARGS__; FN<METRIC, 4, 1, true> GRID_H __VA_ARGS__; } \
+  else if (sh.vec == 4 && sh.nchunk == 2) { FN<METRIC, 4, 2, false> GRID_L __VA_ARGS__; FN<METRIC, 4, 2, true> GRID_H __VA_ARGS__; } \
+  else { FN<METRIC, 4, 4, false> GRID_L __VA_ARGS__; FN<METRIC, 4, 4, true> GRID_H __VA_ARGS__; }
 
+// GRID_L: one warp per row; GRID_H: the heavy-row launch (fixed grid, CTA per heavy row)
+#define GRID_L <<<grid, block, 0, st>>>
+#define GRID_H <<<dim3(HEAVY_GRID), block, 0, st>>>
 #define DISPATCH_METRIC(FN, ...)                                                            \
   switch (metric) {                                                                         \
     case TAGAN_METRIC_SCALED_DOT: { DISPATCH_SHAPE(TAGAN_METRIC_SCALED_DOT, FN, __VA_ARGS__) } break;   \
@@ -448,7 +670,7 @@ TAGAN_API int tagan_geo_attn_fwd_part(const float* Q, int64_t ldq, const float* 
   const int D = H / heads;
   dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), block(WARPS_PER_BLOCK * 32);
   cudaStream_t st = as_stream(stream);
-  DISPATCH_METRIC(geo_attn_fwd_kernel, <<<grid, block, 0, st>>>(Q, ldq, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, attn))
+  DISPATCH_METRIC(geo_attn_fwd_kernel, (Q, ldq, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, attn))
   return tagan_launch_status();
 }
 
@@ -482,13 +704,13 @@ TAGAN_API int tagan_geo_attn_bwd_part(const float* Q, int64_t ldq, const float* 
     const int N = n_rows;
     const int64_t ldd = lddq;
     dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    DISPATCH_METRIC(geo_attn_bwd_row_kernel, <<<grid, block, 0, st>>>(Q, ldq, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, dctx, dQ, ldd, delta_ws, dpr))
+    DISPATCH_METRIC(geo_attn_bwd_row_kernel, (Q, ldq, K, V, ld, rowptr, col, N, heads, D, metric_param, ctx, lse, dctx, dQ, ldd, delta_ws, dpr))
   }
   if (n_src > 0) {
     const int N = n_src;
     const int64_t ldd = lddkv;
     dim3 grid((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    DISPATCH_METRIC(geo_attn_bwd_col_kernel, <<<grid, block, 0, st>>>(Q, ldq, K, V, ld, rowptr_t, row_t, N, heads, D, metric_param, lse, delta_ws, dctx, dK, dV, ldd))
+    DISPATCH_METRIC(geo_attn_bwd_col_kernel, (Q, ldq, K, V, ld, rowptr_t, row_t, N, heads, D, metric_param, lse, delta_ws, dctx, dK, dV, ldd))
   }
   if (want_dparam) reduce_rows_per_head<<<heads, 256, 0, st>>>(dparam_ws, n_rows, heads, dparam);
   return tagan_launch_status();

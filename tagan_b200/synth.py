@@ -34,13 +34,14 @@ WORKLOADS = {
 
 
 def random_edges(num_nodes: int, num_edges: int, gen: torch.Generator, graph: str = "uniform") -> torch.Tensor:
-    """[2,E] int64.  "powerlaw": preferential-attachment-like degree skew (Zipf-ish destination
-    choice, made bidirectional as src/tagan/utils/data_utils.py:69-75 does)."""
+    """[2,E] int64.  "powerlaw": Barabasi-Albert-like degree skew -- the expected degree of the node of
+    rank i is proportional to i^(-1/2) (inverse-CDF sampling hub = N*u^2), i.e. max degree ~ m*sqrt(N) --
+    made bidirectional as src/tagan/utils/data_utils.py:69-75 does."""
     if graph == "uniform":
         return torch.randint(0, num_nodes, (2, num_edges), generator=gen, dtype=torch.int64)
     half = num_edges // 2
     u = torch.rand(half, generator=gen)
-    hub = (u.pow(3.0) * num_nodes).long().clamp_(0, num_nodes - 1)       # skewed towards low ids
+    hub = (u.pow(2.0) * num_nodes).long().clamp_(0, num_nodes - 1)       # skewed towards low ids
     other = torch.randint(0, num_nodes, (half,), generator=gen, dtype=torch.int64)
     src = torch.cat([hub, other])
     dst = torch.cat([other, hub])

@@ -213,6 +213,42 @@ def test_geo_attention_vs_oracle_shapes(dev, hidden, heads, metric):
         torch.testing.assert_close(p.grad.cpu(), gref, **tol, msg=lambda m, k=k: f"d{k}: {m}")
 
 
+@pytest.mark.parametrize("metric", ["euclidean", "scaled_dot_product", "rbf_kernel"])
+def test_geo_attention_hub_rows_and_columns(dev, metric):
+    """Power-law corner: a destination row with ~3000 entries and a source column with ~2500 entries take the
+    CTA-per-row path (8 warps, partial states merged in warp order); everything else the warp-per-row path."""
+    import tagan_b200
+    torch.manual_seed(3)
+    n, e, hidden, heads = 4000, 30000, 128, 8
+    learn = metric == "rbf_kernel"
+    layer = tagan_b200.TAGANGraphAttention(hidden, heads, dropout=0.0, distance_metric=metric,
+                                           learnable_distance=learn).to(dev)
+    x = torch.randn(n, hidden) * 0.5
+    ei = torch.randint(0, n, (2, e))
+    ei[0, :3000] = 17                       # hub destination row
+    ei[1, 3000:5500] = 23                   # hub source column
+    ei[0, 6000:6200] = 99                   # row just above the threshold
+    wout = torch.randn(n, hidden)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.geometric_attention.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    ref, aref = R.geo_attention(xr, sd, ei, heads, metric, learnable_distance=learn, return_attn=True)
+    (ref * wout).sum().backward()
+    xd = x.to(dev).requires_grad_(True)
+    out, w = layer(xd, ei.to(dev), None, return_attention_weights=True)
+    (out * wout.to(dev)).sum().backward()
+    _close(out.detach().cpu(), ref.detach())
+    _close(w["edge_attention"].detach().cpu(), aref.detach())
+    _close(xd.grad.cpu(), xr.grad)
+    for k, p in layer.geometric_attention.named_parameters():
+        gref = sd[k].grad
+        torch.testing.assert_close(p.grad.cpu(), gref, **_gtol(k, gref, metric), msg=lambda m, k=k: f"d{k}: {m}")
+    # deterministic
+    xd2 = x.to(dev).requires_grad_(True)
+    out2 = layer(xd2, ei.to(dev))
+    (out2 * wout.to(dev)).sum().backward()
+    assert torch.equal(out2, out) and torch.equal(xd2.grad, xd.grad)
+
+
 def test_geo_attention_full_size_properties(dev):
     """Config-3 snapshot (100k nodes, 2M edges, H=128, h=8): size-independent properties --
     weights of every row sum to 1, the result is bit-identical run to run (no atomics), the
