@@ -241,7 +241,9 @@ def test_geo_attention_hub_rows_and_columns(dev, metric):
     _close(xd.grad.cpu(), xr.grad)
     for k, p in layer.geometric_attention.named_parameters():
         gref = sd[k].grad
-        torch.testing.assert_close(p.grad.cpu(), gref, **_gtol(k, gref, metric), msg=lambda m, k=k: f"d{k}: {m}")
+        tol = _gtol(k, gref, metric)
+        tol["atol"] *= 3.0          # hub rows sum thousands of terms into one row's gradient: 3e-5 of the gradient scale
+        torch.testing.assert_close(p.grad.cpu(), gref, **tol, msg=lambda m, k=k: f"d{k}: {m}")
     # deterministic
     xd2 = x.to(dev).requires_grad_(True)
     out2 = layer(xd2, ei.to(dev))
