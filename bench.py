@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bank", action="store_true")
+    ap.add_argument("--cuda-profiler", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -223,11 +225,15 @@ def run_ours(args):
     ops.CALLS["n"] = 0
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
         step(xs_d, eis_d)
     ev1.record()
     barrier()
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
     prof, ops.PROFILE = ops.PROFILE, None
     launches = ops.CALLS["n"]
     clocks = sampler.stop() if rank == 0 else None

@@ -219,18 +219,19 @@ int tagan_tattn_mask_allones(const float* ts, int64_t batch, int32_t T, float ba
  *       u,r = sigmoid(W[c,p]);  rp = r*p;  cand = tanh(Wo[c,rp]);  out = (1-u)*c + u*cand (+c)
  * `second` is the gated half of the concatenation (h^ / p), `base` the blended one (h^ / c).
  * ------------------------------------------------------------------------------------- */
-/* g[rows,2H] = [reset | update] pre-activations -> r, z = sigmoid; rs[:, :] = r * second */
-int tagan_gates_fwd(const float* g, const float* second, int64_t lds, float* r, float* z,
+/* g[rows, >=2H] (row stride ldg) = [reset | update] pre-activations -> r, z = sigmoid; rs = r * second.
+ * The strides let g / cand_pre be column slices of one fused [rows,3H] pre-activation buffer. */
+int tagan_gates_fwd(const float* g, int64_t ldg, const float* second, int64_t lds, float* r, float* z,
                     float* rs, int64_t ldrs, int64_t rows, int32_t H, tagan_stream_t stream);
 int tagan_gates_bwd(const float* drs, int64_t lddrs, const float* dz, const float* r, const float* z,
-                    const float* second, int64_t lds, float* dg, float* dsecond, int64_t ldds,
+                    const float* second, int64_t lds, float* dg, int64_t lddg, float* dsecond, int64_t ldds,
                     int32_t accumulate, int64_t rows, int32_t H, tagan_stream_t stream);
 /* cand = tanh(cand_pre); out = (1-z)*base + z*cand (+ base if residual) */
-int tagan_blend_fwd(const float* cand_pre, const float* z, const float* base, int64_t ldb,
+int tagan_blend_fwd(const float* cand_pre, int64_t ldc, const float* z, const float* base, int64_t ldb,
                     float* cand, float* out, int32_t residual, int64_t rows, int32_t H,
                     tagan_stream_t stream);
 int tagan_blend_bwd(const float* dout, const float* z, const float* cand, const float* base, int64_t ldb,
-                    float* dcand_pre, float* dz, float* dbase, int64_t lddb, int32_t accumulate,
+                    float* dcand_pre, int64_t lddc, float* dz, float* dbase, int64_t lddb, int32_t accumulate,
                     int32_t residual, int64_t rows, int32_t H, tagan_stream_t stream);
 /* sliding window over the snapshot axis of p[T, inner] (TemporalSkipConnection.forward :880-926):
  * out[t] = agg_{u in [max(0,t-w), min(T,t+w+1))} p[u];  agg: 0 mean, 1 max, 2 sum. */

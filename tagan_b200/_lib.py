@@ -48,10 +48,10 @@ SIGNATURES = {
     "tagan_tattn_bwd": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _i64, _p, _i32, _f32, _p,
                                _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _sz, _p]),
     "tagan_tattn_mask_allones": (_i32, [_p, _i64, _i32, _f32, _p, _i64, _p, _p]),
-    "tagan_gates_fwd": (_i32, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _i32, _p]),
-    "tagan_gates_bwd": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i32, _i64, _i32, _p]),
-    "tagan_blend_fwd": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _i32, _p]),
-    "tagan_blend_bwd": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i64, _i32, _p]),
+    "tagan_gates_fwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i64, _i32, _p]),
+    "tagan_gates_bwd": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i32, _p]),
+    "tagan_blend_fwd": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _i32, _i64, _i32, _p]),
+    "tagan_blend_bwd": (_i32, [_p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _i64, _i32, _p]),
     "tagan_skip_window_fwd": (_i32, [_p, _p, _i32, _i64, _i32, _i32, _p]),
     "tagan_skip_window_bwd": (_i32, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _p]),
     "tagan_bank_gather": (_i32, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p]),

@@ -16,15 +16,15 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // g [rows,2H] pre-activations (first H: blend gate z/u ... see `gate_first`): the reference
 // concatenates nothing here -- two separate Linears -- so the caller packs [W_a; W_b] as it likes.
 // Layout used by the host: g[:, :H] = reset pre-activation, g[:, H:] = update pre-activation.
-__global__ void gates_fwd_kernel(const float* __restrict__ g, const float* __restrict__ second, int64_t lds,
+__global__ void gates_fwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ second, int64_t lds,
                                  float* __restrict__ r, float* __restrict__ z, float* __restrict__ rs, int64_t ldrs,
                                  int64_t rows, int H) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
   int64_t row = i / H;
   int c = (int)(i - row * H);
-  float rv = sigmoidf_(g[row * 2 * H + c]);
-  float zv = sigmoidf_(g[row * 2 * H + H + c]);
+  float rv = sigmoidf_(g[row * ldg + c]);
+  float zv = sigmoidf_(g[row * ldg + H + c]);
   r[i] = rv;
   z[i] = zv;
   rs[row * ldrs + c] = rv * second[row * lds + c];
@@ -33,29 +33,29 @@ __global__ void gates_fwd_kernel(const float* __restrict__ g, const float* __res
 // dg[:, :H] = d(rs)*second * r(1-r);  dg[:, H:] = dz * z(1-z);  dsecond (+)= d(rs)*r
 __global__ void gates_bwd_kernel(const float* __restrict__ drs, int64_t lddrs, const float* __restrict__ dz,
                                  const float* __restrict__ r, const float* __restrict__ z,
-                                 const float* __restrict__ second, int64_t lds, float* __restrict__ dg,
+                                 const float* __restrict__ second, int64_t lds, float* __restrict__ dg, int64_t lddg,
                                  float* __restrict__ dsecond, int64_t ldds, int accumulate, int64_t rows, int H) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
   int64_t row = i / H;
   int c = (int)(i - row * H);
   float rv = r[i], zv = z[i], d = drs[row * lddrs + c];
-  dg[row * 2 * H + c] = d * second[row * lds + c] * rv * (1.f - rv);
-  dg[row * 2 * H + H + c] = dz[i] * zv * (1.f - zv);
+  dg[row * lddg + c] = d * second[row * lds + c] * rv * (1.f - rv);
+  dg[row * lddg + H + c] = dz[i] * zv * (1.f - zv);
   float* o = dsecond + row * ldds + c;
   float v = d * rv;
   *o = accumulate ? *o + v : v;
 }
 
 // cand = tanh(cpre); out = (1-z)*base + z*cand (+ base if residual)
-__global__ void blend_fwd_kernel(const float* __restrict__ cpre, const float* __restrict__ z,
+__global__ void blend_fwd_kernel(const float* __restrict__ cpre, int64_t ldc, const float* __restrict__ z,
                                  const float* __restrict__ base, int64_t ldb, float* __restrict__ cand,
                                  float* __restrict__ out, int residual, int64_t rows, int H) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
   int64_t row = i / H;
   int c = (int)(i - row * H);
-  float t = tanhf(cpre[i]);
+  float t = tanhf(cpre[row * ldc + c]);
   float zv = z[i], b = base[row * ldb + c];
   cand[i] = t;
   float o = (1.f - zv) * b + zv * t;
@@ -65,14 +65,14 @@ __global__ void blend_fwd_kernel(const float* __restrict__ cpre, const float* __
 // dcpre = dout*z*(1-cand^2); dz = dout*(cand-base); dbase (+)= dout*(1-z) (+ dout if residual)
 __global__ void blend_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z,
                                  const float* __restrict__ cand, const float* __restrict__ base, int64_t ldb,
-                                 float* __restrict__ dcpre, float* __restrict__ dz, float* __restrict__ dbase,
+                                 float* __restrict__ dcpre, int64_t lddc, float* __restrict__ dz, float* __restrict__ dbase,
                                  int64_t lddb, int accumulate, int residual, int64_t rows, int H) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
   int64_t row = i / H;
   int c = (int)(i - row * H);
   float d = dout[i], zv = z[i], t = cand[i], b = base[row * ldb + c];
-  dcpre[i] = d * zv * (1.f - t * t);
+  dcpre[row * lddc + c] = d * zv * (1.f - t * t);
   dz[i] = d * (t - b);
   float v = d * (1.f - zv) + (residual ? d : 0.f);
   float* o = dbase + row * lddb + c;
@@ -139,40 +139,41 @@ __global__ void window_bwd_kernel(const float* __restrict__ dg, const float* __r
 
 }  // namespace
 
-TAGAN_API int tagan_gates_fwd(const float* g, const float* second, int64_t lds, float* r, float* z, float* rs,
-                              int64_t ldrs, int64_t rows, int32_t H, tagan_stream_t stream) {
-  if (!g || !second || !r || !z || !rs || rows < 0 || H <= 0) return TAGAN_E_INVALID;
+TAGAN_API int tagan_gates_fwd(const float* g, int64_t ldg, const float* second, int64_t lds, float* r, float* z,
+                              float* rs, int64_t ldrs, int64_t rows, int32_t H, tagan_stream_t stream) {
+  if (!g || !second || !r || !z || !rs || rows < 0 || H <= 0 || ldg < 2 * H) return TAGAN_E_INVALID;
   if (rows == 0) return 0;
-  gates_fwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(g, second, lds, r, z, rs, ldrs, rows, H);
+  gates_fwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(g, ldg, second, lds, r, z, rs, ldrs, rows, H);
   return tagan_launch_status();
 }
 
 TAGAN_API int tagan_gates_bwd(const float* drs, int64_t lddrs, const float* dz, const float* r, const float* z,
-                              const float* second, int64_t lds, float* dg, float* dsecond, int64_t ldds,
-                              int32_t accumulate, int64_t rows, int32_t H, tagan_stream_t stream) {
-  if (!drs || !dz || !r || !z || !second || !dg || !dsecond || rows < 0 || H <= 0) return TAGAN_E_INVALID;
+                              const float* second, int64_t lds, float* dg, int64_t lddg, float* dsecond,
+                              int64_t ldds, int32_t accumulate, int64_t rows, int32_t H, tagan_stream_t stream) {
+  if (!drs || !dz || !r || !z || !second || !dg || !dsecond || rows < 0 || H <= 0 || lddg < 2 * H) return TAGAN_E_INVALID;
   if (rows == 0) return 0;
   gates_bwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(drs, lddrs, dz, r, z, second, lds, dg,
-                                                                               dsecond, ldds, accumulate, rows, H);
+                                                                               lddg, dsecond, ldds, accumulate, rows, H);
   return tagan_launch_status();
 }
 
-TAGAN_API int tagan_blend_fwd(const float* cand_pre, const float* z, const float* base, int64_t ldb, float* cand,
-                              float* out, int32_t residual, int64_t rows, int32_t H, tagan_stream_t stream) {
-  if (!cand_pre || !z || !base || !cand || !out || rows < 0 || H <= 0) return TAGAN_E_INVALID;
+TAGAN_API int tagan_blend_fwd(const float* cand_pre, int64_t ldc, const float* z, const float* base, int64_t ldb,
+                              float* cand, float* out, int32_t residual, int64_t rows, int32_t H,
+                              tagan_stream_t stream) {
+  if (!cand_pre || !z || !base || !cand || !out || rows < 0 || H <= 0 || ldc < H) return TAGAN_E_INVALID;
   if (rows == 0) return 0;
-  blend_fwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(cand_pre, z, base, ldb, cand, out,
+  blend_fwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(cand_pre, ldc, z, base, ldb, cand, out,
                                                                                residual, rows, H);
   return tagan_launch_status();
 }
 
 TAGAN_API int tagan_blend_bwd(const float* dout, const float* z, const float* cand, const float* base, int64_t ldb,
-                              float* dcand_pre, float* dz, float* dbase, int64_t lddb, int32_t accumulate,
-                              int32_t residual, int64_t rows, int32_t H, tagan_stream_t stream) {
-  if (!dout || !z || !cand || !base || !dcand_pre || !dz || !dbase || rows < 0 || H <= 0) return TAGAN_E_INVALID;
+                              float* dcand_pre, int64_t lddc, float* dz, float* dbase, int64_t lddb,
+                              int32_t accumulate, int32_t residual, int64_t rows, int32_t H, tagan_stream_t stream) {
+  if (!dout || !z || !cand || !base || !dcand_pre || !dz || !dbase || rows < 0 || H <= 0 || lddc < H) return TAGAN_E_INVALID;
   if (rows == 0) return 0;
-  blend_bwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(dout, z, cand, base, ldb, dcand_pre, dz,
-                                                                               dbase, lddb, accumulate, residual, rows, H);
+  blend_bwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(dout, z, cand, base, ldb, dcand_pre, lddc,
+                                                                               dz, dbase, lddb, accumulate, residual, rows, H);
   return tagan_launch_status();
 }
 

@@ -404,6 +404,11 @@ class TemporalEvolutionLayer(nn.Module):
         nn.init.zeros_(self.output_projection.bias)
 
     def _scan(self, cell, xs3, ts, order, reverse):
+        if not (self.training and cell.dropout > 0):
+            # fused recurrence (tagan_b200/gru.py); the step-by-step composition below is kept for
+            # training with dropout, whose mask sits between the blend and LayerNorm_out (:542-546)
+            from .gru import gru_scan
+            return gru_scan(xs3, ts if self.time_aware else None, cell, reverse)
         t_steps = xs3.shape[0]
         n = xs3.shape[1]
         g, b = _ln_args(cell, "layer_norm_x", cell.use_layer_norm)
@@ -423,12 +428,14 @@ class TemporalEvolutionLayer(nn.Module):
         """xs3 ``[T,N,in]`` -> ``[T,N,hidden]`` (:648-755)."""
         t_steps, n, _ = xs3.shape
         ts = time_stamps.float().contiguous() if time_stamps is not None else None
-        fwd = self._scan(self.forward_cell, xs3, ts, list(range(t_steps)), False)
+        def stacked(v):
+            return v if isinstance(v, torch.Tensor) else torch.stack(v)
+        fwd = stacked(self._scan(self.forward_cell, xs3, ts, list(range(t_steps)), False))
         if self.bidirectional:
-            bwd = self._scan(self.backward_cell, xs3, ts, list(range(t_steps - 1, -1, -1)), True)
-            s = torch.cat([torch.stack(fwd), torch.stack(bwd)], dim=-1)
+            bwd = stacked(self._scan(self.backward_cell, xs3, ts, list(range(t_steps - 1, -1, -1)), True))
+            s = torch.cat([fwd, bwd], dim=-1)
         else:
-            s = torch.stack(fwd)
+            s = fwd
         o = ops.linear(s.view(t_steps * n, -1), self.output_projection.weight, self.output_projection.bias)
         o = self.dropout_layer(o)
         res = xs3.reshape(t_steps * n, -1) if (self.residual and self.input_dim == self.hidden_dim) else None

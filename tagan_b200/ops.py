@@ -44,9 +44,10 @@ class _timed:
             PROFILE.setdefault(self.name, []).append((self.s, self.e))
 
 
-def _ptr(t: Optional[torch.Tensor]):
-    if t is None:
-        return None
+def _ptr(t):
+    """Device pointer of a tensor (or a raw ``c_void_p`` passed through)."""
+    if t is None or isinstance(t, C.c_void_p):
+        return t
     if not t.is_cuda:
         raise RuntimeError("tagan_b200 has no CPU path: tensor must live on a CUDA device")
     return C.c_void_p(t.data_ptr())
@@ -153,7 +154,8 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int, transpose: bool = True, 
 def gemm(op: int, m: int, n: int, k: int, a, lda, b, ldb, bias, c, ldc, accumulate=False):
     lib = _lib.load()
     nbytes = lib.tagan_gemm_workspace_bytes(op, m, n, k)
-    ws = workspace(nbytes, c.device) if nbytes else None
+    dev = c.device if isinstance(c, torch.Tensor) else torch.device("cuda", torch.cuda.current_device())
+    ws = workspace(nbytes, dev) if nbytes else None
     with _timed("gemm"):
         rc = lib.tagan_gemm(op, m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(bias), _ptr(c), ldc, int(accumulate),
                             GEMM_PRECISION, _ptr(ws), ws.numel() if ws is not None else 0, _stream())
@@ -490,7 +492,7 @@ class _GatesFn(torch.autograd.Function):
         r = torch.empty(rows, h, dtype=torch.float32, device=g.device)
         z = torch.empty_like(r)
         rs = torch.empty_like(r)
-        _lib.check(lib.tagan_gates_fwd(_ptr(g2), _ptr(s2), lds, _ptr(r), _ptr(z), _ptr(rs), h, rows, h, _stream()),
+        _lib.check(lib.tagan_gates_fwd(_ptr(g2), 2 * h, _ptr(s2), lds, _ptr(r), _ptr(z), _ptr(rs), h, rows, h, _stream()),
                    "tagan_gates_fwd")
         CALLS["n"] += 1
         ctx.save_for_backward(r, z, s2)
@@ -506,7 +508,7 @@ class _GatesFn(torch.autograd.Function):
         dz = _f32c(dz).contiguous()
         dg = torch.empty(rows, 2 * h, dtype=torch.float32, device=r.device)
         dsecond = torch.empty(rows, h, dtype=torch.float32, device=r.device)
-        _lib.check(lib.tagan_gates_bwd(_ptr(drs), h, _ptr(dz), _ptr(r), _ptr(z), _ptr(s2), lds, _ptr(dg),
+        _lib.check(lib.tagan_gates_bwd(_ptr(drs), h, _ptr(dz), _ptr(r), _ptr(z), _ptr(s2), lds, _ptr(dg), 2 * h,
                                        _ptr(dsecond), h, 0, rows, h, _stream()), "tagan_gates_bwd")
         CALLS["n"] += 1
         return dg, dsecond
@@ -524,7 +526,7 @@ class _BlendFn(torch.autograd.Function):
         b2, _, _, ldb = _rows(base)
         cand = torch.empty(rows, h, dtype=torch.float32, device=c2.device)
         out = torch.empty_like(cand)
-        _lib.check(lib.tagan_blend_fwd(_ptr(c2), _ptr(z2), _ptr(b2), ldb, _ptr(cand), _ptr(out), int(residual), rows, h,
+        _lib.check(lib.tagan_blend_fwd(_ptr(c2), h, _ptr(z2), _ptr(b2), ldb, _ptr(cand), _ptr(out), int(residual), rows, h,
                                        _stream()), "tagan_blend_fwd")
         CALLS["n"] += 1
         ctx.save_for_backward(z2, cand, b2)
@@ -541,7 +543,7 @@ class _BlendFn(torch.autograd.Function):
         dc = torch.empty_like(cand)
         dz = torch.empty_like(cand)
         db = torch.empty_like(cand)
-        _lib.check(lib.tagan_blend_bwd(_ptr(dout), _ptr(z2), _ptr(cand), _ptr(b2), ldb, _ptr(dc), _ptr(dz), _ptr(db), h,
+        _lib.check(lib.tagan_blend_bwd(_ptr(dout), _ptr(z2), _ptr(cand), _ptr(b2), ldb, _ptr(dc), h, _ptr(dz), _ptr(db), h,
                                        0, int(ctx.residual), rows, h, _stream()), "tagan_blend_bwd")
         CALLS["n"] += 1
         return dc, dz, db, None

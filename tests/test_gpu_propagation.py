@@ -132,3 +132,57 @@ def test_propagation_core_vs_oracle(dev, n, t, hidden):
         if gref is None:
             continue
         torch.testing.assert_close(p.grad.cpu(), gref, **_gtol(gref), msg=lambda m, k=k: f"d{k}: {m}")
+
+
+def test_bidirectional_evolution_vs_torch_composition(dev):
+    """bidirectional=True (temporal_propagation.py:690-733): fused scan in both directions against the same
+    arithmetic composed from torch ops on the GPU tensors (the oracle restates the unidirectional case)."""
+    import tagan_b200
+    import torch.nn.functional as F
+    torch.manual_seed(5)
+    n, t, hidden = 300, 7, 64
+    ev = tagan_b200.TemporalEvolutionLayer(hidden, hidden, dropout=0.0, bidirectional=True).to(dev)
+    xs = [torch.randn(n, hidden, device=dev, requires_grad=True) for _ in range(t)]
+    ts = torch.cumsum(torch.rand(n, t, device=dev) * 2.0, 1)
+    wout = torch.randn(t, n, hidden, device=dev)
+
+    def cell_ref(cell, x, h, td):
+        sd = {k: v for k, v in cell.state_dict().items()}
+        x = F.layer_norm(x, (x.shape[-1],), sd["layer_norm_x.weight"], sd["layer_norm_x.bias"])
+        if h is None:
+            h = torch.zeros(x.shape[0], cell.hidden_dim, device=x.device)
+        else:
+            h = F.layer_norm(h, (h.shape[-1],), sd["layer_norm_h.weight"], sd["layer_norm_h.bias"])
+        if td is not None:
+            h = h * torch.exp(-torch.clamp(td, 0.0, 10.0)).unsqueeze(1)
+        xh = torch.cat([x, h], -1)
+        r = torch.sigmoid(F.linear(xh, sd["reset_gate.weight"], sd["reset_gate.bias"]))
+        z = torch.sigmoid(F.linear(xh, sd["update_gate.weight"], sd["update_gate.bias"]))
+        ht = torch.tanh(F.linear(torch.cat([x, r * h], -1), sd["candidate.weight"], sd["candidate.bias"]))
+        hn = (1 - z) * h + z * ht
+        return F.layer_norm(hn, (hn.shape[-1],), sd["layer_norm_out.weight"], sd["layer_norm_out.bias"])
+
+    xr = [x.detach().clone().requires_grad_(True) for x in xs]
+    hf, fstates = None, []
+    for i in range(t):
+        hf = cell_ref(ev.forward_cell, xr[i], hf, ts[:, i] - ts[:, i - 1] if i > 0 else None)
+        fstates.append(hf)
+    hb, bstates = None, [None] * t
+    for i in range(t - 1, -1, -1):
+        hb = cell_ref(ev.backward_cell, xr[i], hb, ts[:, i + 1] - ts[:, i] if i < t - 1 else None)
+        bstates[i] = hb
+    refs = []
+    for i in range(t):
+        o = F.linear(torch.cat([fstates[i], bstates[i]], 1), ev.output_projection.weight, ev.output_projection.bias) + xr[i]
+        refs.append(F.layer_norm(o, (hidden,), ev.layer_norm.weight, ev.layer_norm.bias))
+    ref = torch.stack(refs)
+    (ref * wout).sum().backward()
+    gref = {k: p.grad.clone() for k, p in ev.named_parameters()}
+    ev.zero_grad()
+    out = torch.stack(ev(xs, ts))
+    (out * wout).sum().backward()
+    _close(out.detach().cpu(), ref.detach().cpu())
+    for a, b in zip(xs, xr):
+        _close(a.grad.cpu(), b.grad.cpu())
+    for k, p in ev.named_parameters():
+        torch.testing.assert_close(p.grad.cpu(), gref[k].cpu(), **_gtol(gref[k].cpu()), msg=lambda m, k=k: f"d{k}: {m}")
