@@ -147,7 +147,7 @@ def test_bidirectional_evolution_vs_torch_composition(dev):
     wout = torch.randn(t, n, hidden, device=dev)
 
     def cell_ref(cell, x, h, td):
-        sd = {k: v for k, v in cell.state_dict().items()}
+        sd = dict(cell.named_parameters())
         x = F.layer_norm(x, (x.shape[-1],), sd["layer_norm_x.weight"], sd["layer_norm_x.bias"])
         if h is None:
             h = torch.zeros(x.shape[0], cell.hidden_dim, device=x.device)
