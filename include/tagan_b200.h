@@ -157,7 +157,9 @@ int tagan_colsum(const float* x, int64_t ldx, float* out, void* workspace, size_
  *   NT: C[M,N] = A[M,K] . B[N,K]^T (+ bias[N]) (+ C if accumulate)        forward Linear
  *   NN: C[M,N] = A[M,K] . B[K,N]            (+ C if accumulate)           dX = dY . W
  *   TN: C[M,N] = A[Kd,M]^T . B[Kd,N]        (+ C if accumulate)           dW = dY^T . X
- * fp32 in/out.  precision: 0 = fp32 FFMA, 1 = 3xTF32 on tcgen05 (fp32-accurate), 2 = 1xTF32.
+ * fp32 in/out.  precision: 0 = fp32 FFMA, 1 = TF32 hi/lo split on tcgen05 (3 MMAs, fp32-accurate),
+ * 2 = plain TF32, 3 = hi/lo split with the lo.lo term as well (4 MMAs);
+ * +4 forces the LDG-fed tensor-core kernel instead of the TMA-fed one (TMA needs 16-byte aligned operands).
  * ------------------------------------------------------------------------------------- */
 size_t tagan_gemm_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k);
 int tagan_gemm(int32_t op /*0=NT,1=NN,2=TN*/, int64_t m, int64_t n, int64_t k,

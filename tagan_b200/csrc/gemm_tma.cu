@@ -1,43 +1,37 @@
-// Dense projections on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-accurate via 3xTF32.
+// Dense projections on tcgen05 + TMEM, TMA-fed (the preferred path; gemm_tc.cu is the fallback for operands
+// that TMA cannot address: unaligned base pointers or leading dimensions).
 //
-//   C[M,N] = op(A) . op(B)   NT: A[M,K],B[N,K] (nn.Linear forward)   NN: A[M,K],B[K,N] (dX = dY.W)
-//                            TN: A[K,M],B[K,N] (dW = dY^T.X, split-K, fixed-order reduction)
+//   C[M,N] = op(A) . op(B)   NT / NN / TN as in gemm_tc.cu, fp32-accurate through the TF32 hi/lo split.
 //
-// The reference's projections are fp32 nn.Linear; parity is rtol 1e-4 / atol 1e-5, which plain TF32
-// (10-bit mantissa) misses.  Every fp32 operand is split on the fly into hi = rn_tf32(x) and lo = rn_tf32(x - hi) (both exactly
-// representable in TF32, unbiased), and D += Alo.Blo + Alo.Bhi + Ahi.Blo + Ahi.Bhi is
-// accumulated in fp32 in TMEM (the MMA pipe is far from being the bottleneck, so the lo.lo term is kept).
-//
-// Persistent, warp-specialised CTA (one per SM), 128x128 output tiles, BK = 32 floats = one 128-byte
-// swizzle row, 3-stage smem ring, 2 accumulator stages in TMEM (256 columns):
-//   warps 0-3   epilogue : tcgen05.ld 32 lanes x 32 columns -> +bias/+C -> global (row-contiguous 128 B runs)
-//   warp  4     MMA      : one elected thread issues tcgen05.mma.kind::tf32 (3 per k-step) and tcgen05.commit
-//   warps 5-20  producers (two groups of 8 warps alternating k-blocks): coalesced 128-bit global loads -> hi/lo split -> st.shared into the canonical
-//                          SWIZZLE_128B UMMA layouts (K-major or MN-major, so no transposes are ever
-//                          materialised) -> fence.proxy.async -> mbarrier arrive
-// With K <= 512 and N <= 768 these GEMMs sit at ~140 flop/byte even at 3x work, i.e. they are HBM-bound
-// once on tensor cores; the producers are sized to stream A at HBM rate while B (weights) stays in L2.
+// Warp roles of the persistent CTA (one per SM, 14 warps):
+//   warps 0-3   epilogue  : tcgen05.ld -> padded smem -> row-contiguous 128 B stores (+bias / +C)
+//   warp  4     MMA       : one thread issues tcgen05.mma.kind::tf32 (lo.lo, lo.hi, hi.lo, hi.hi per k-step)
+//   warp  5     TMA       : one thread issues cp.async.bulk.tensor loads of the raw fp32 A/B tiles straight
+//                           into their final 128B-swizzled positions (K-major: one 128x32 box with
+//                           SWIZZLE_128B; MN-major: four 32x32 boxes with SWIZZLE_128B_ATOM_32B), completing
+//                           on an mbarrier with expect_tx; it runs up to STAGES k-blocks ahead, so the HBM
+//                           stream is never exposed to thread-level latency and costs no registers
+//   warps 6-13  split     : smem -> smem, layout-agnostic: hi = rn_tf32(x) in place, lo = rn_tf32(x - hi) into
+//                           the twin tile, fence.proxy.async, arrive on the stage's "full" barrier
+// Out-of-range rows / columns / K tail are zero-filled by TMA itself, so there is no edge-tile code path.
 #include "common.cuh"
+#include <cuda.h>
 
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
-constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB (A and B tiles have the same size)
+constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
-constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
-constexpr int MMA_WARP = EPI_WARPS;                     // warp 4
-constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;   // 416
-constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int PROD_GROUPS = 2;                          // groups alternate k-blocks: TLP hides the load latency
-constexpr int GROUP_WARPS = PROD_WARPS / PROD_GROUPS;   // 8 warps = 256 threads per group
-constexpr int TMEM_COLS = ACC_STAGES * BN;              // 256
-constexpr int EPI_PITCH = 36;                           // floats; 144-byte rows keep the staging tile conflict-free
-constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH * 4;     // per epilogue warp
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ +
-                              (size_t)EPI_WARPS * EPI_STAGE_BYTES;
-
+constexpr int EPI_WARPS = 4, SPLIT_WARPS = 8;
+constexpr int MMA_WARP = EPI_WARPS, TMA_WARP = EPI_WARPS + 1, SPLIT_WARP0 = EPI_WARPS + 2;
+constexpr int THREADS = (EPI_WARPS + 2 + SPLIT_WARPS) * 32;   // 448
+constexpr int SPLIT_THREADS = SPLIT_WARPS * 32;
+constexpr int TMEM_COLS = ACC_STAGES * BN;
+constexpr int EPI_PITCH = 36;
+constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH * 4;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + (size_t)EPI_WARPS * EPI_STAGE_BYTES;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -80,71 +74,43 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
-// Canonical SWIZZLE_128B tile offsets (bytes) for a [128 mn x 32 k] fp32 tile.
-//   K-major : 8-row groups of 128-byte rows (k contiguous), 16-byte chunk index XOR (row % 8); SBO = 1024.
-//   MN-major (SWIZZLE_128B_BASE32B, Swizzle<2,5,2>): atoms of 4 k-rows x 128 bytes (32 mn contiguous), the
-//             32-byte chunk index XOR (k % 4); k-atoms 512 B apart (SBO), mn-blocks of 32 floats 4096 B apart (LBO).
-__device__ __forceinline__ uint32_t off_kmajor(int mn, int kchunk /*k/4*/) {
-  return (uint32_t)((mn >> 3) * 1024 + (mn & 7) * 128 + ((kchunk ^ (mn & 7)) << 4));
-}
-__device__ __forceinline__ uint32_t off_mnmajor(int mnchunk /*mn/4*/, int k) {
-  const int c16 = mnchunk & 7;                     // 16-byte chunk inside the 128-byte row
-  return (uint32_t)((mnchunk >> 3) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((c16 >> 1) ^ (k & 3)) << 5) | ((c16 & 1) << 4)));
-}
-
-// Round-to-nearest TF32 (unbiased: a truncating split would accumulate a systematic error ~K*2^-22).
 // Same result as cvt.rna.tf32.f32 (nearest, ties away from zero) with two full-rate integer ops.
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
-// hi = rn_tf32(x), lo = rn_tf32(x - hi): both exactly representable, so the tensor core's own
-// fp32->tf32 conversion is the identity and every product is exact.
-__device__ __forceinline__ void split_store(char* hi_tile, char* lo_tile, uint32_t off, float4 v) {
-  float4 h, l;
-  h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
-  l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
-}
 
-// element-wise guarded load of 4 consecutive floats along the contiguous dimension
-__device__ __forceinline__ float4 load4(const float* __restrict__ base, int64_t row, int64_t ld, int64_t col, int64_t nrows,
-                                        int64_t ncols, bool vec_ok) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row < nrows) {
-    const float* p = base + row * ld + col;
-    if (vec_ok && col + 3 < ncols) {
-      v = __ldg(reinterpret_cast<const float4*>(p));
-    } else {
-      if (col < ncols) v.x = __ldg(p);
-      if (col + 1 < ncols) v.y = __ldg(p + 1);
-      if (col + 2 < ncols) v.z = __ldg(p + 2);
-      if (col + 3 < ncols) v.w = __ldg(p + 3);
-    }
-  }
-  return v;
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load: box at element coordinates (c0 = contiguous dim, c1 = row) -> swizzled smem tile
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
 }
 
 struct Params {
   int64_t M, N, K;
-  const float* A; int64_t lda;
-  const float* B; int64_t ldb;
   const float* bias;
   float* C; int64_t ldc;
-  float* partial;          // split-K partial tiles [splits][M][N] or null
+  float* partial;
   int accumulate;
   int a_mn_major, b_mn_major;
   int tiles_m, tiles_n, splits;
   int64_t k_per_split;
-  int a_vec, b_vec, c_vec;
-  int passes;              // 4 / 3 (without lo.lo) / 1 (plain TF32)
+  int c_vec;
+  int passes;              // 4: lo.lo + lo.hi + hi.lo + hi.hi, 3: without lo.lo, 1: plain TF32
+  int b_presplit;          // B arrives already split (tmB = hi image, tmB2 = lo image): only A is split in-kernel
   uint32_t idesc;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmB2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* raw_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* full_bar = raw_bar + STAGES;
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
@@ -153,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], GROUP_WARPS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_bar[s], 1); mbar_init(&full_bar[s], SPLIT_WARPS); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     fence_barrier_init();
   }
@@ -161,90 +127,82 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == TMA_WARP && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
   const int64_t num_work = (int64_t)p.tiles_m * p.tiles_n * p.splits;
 
-  if (warp > MMA_WARP) {
-    // ============================== producers ==============================
-    // 512 threads share the 2048 float4 chunks of a k-block (A tile + B tile).  Global loads run two
-    // k-blocks ahead of the shared-memory stores through a 3-deep register ring (across tile
-    // boundaries too), so ~64 KB per SM are in flight and the A stream is not latency-bound.
-    // Two groups of 8 warps; group g produces k-blocks g, g+2, g+4, ... of this CTA's sequence (across
-    // tile boundaries).  A group issues its 8 loads per thread, waits for the stage to be free, splits and
-    // stores, then arrives on the stage's full barrier.  While one group waits on HBM the other one stores,
-    // so two k-blocks (64 KB) are always in flight without any register-resident prefetch ring.
-    const int group = (warp - (MMA_WARP + 1)) / GROUP_WARPS;
-    const int pt = (threadIdx.x - (MMA_WARP + 1) * 32) % (GROUP_WARPS * 32);      // 0..255 inside the group
-    const int kb_per_split = (int)(p.k_per_split / BK);
-    const int kb_total = (int)((p.K + BK - 1) / BK);
-    const int nwork = (int)num_work;
-    // chunk i (0..3) of a tile for this thread: K-major: row (pt>>3)+32i, 16-byte k-chunk pt&7;
-    // MN-major: k row (pt>>5)+8i, 16-byte mn-chunk pt&31.  smem / global offsets are affine in i.
-    const uint32_t sa0 = p.a_mn_major ? off_mnmajor(pt & 31, pt >> 5) : off_kmajor(pt >> 3, pt & 7);
-    const uint32_t sb0 = 2u * TILE_BYTES + (p.b_mn_major ? off_mnmajor(pt & 31, pt >> 5) : off_kmajor(pt >> 3, pt & 7));
-    const uint32_t sas = p.a_mn_major ? 1024u : 4096u, sbs = p.b_mn_major ? 1024u : 4096u;
-    const int64_t ga0 = p.a_mn_major ? (int64_t)(pt >> 5) * p.lda + (pt & 31) * 4 : (int64_t)(pt >> 3) * p.lda + (pt & 7) * 4;
-    const int64_t gb0 = p.b_mn_major ? (int64_t)(pt >> 5) * p.ldb + (pt & 31) * 4 : (int64_t)(pt >> 3) * p.ldb + (pt & 7) * 4;
-    const int64_t gas = (p.a_mn_major ? 8 : 32) * p.lda, gbs = (p.b_mn_major ? 8 : 32) * p.ldb;
-    const int64_t a_kstep = p.a_mn_major ? (int64_t)BK * p.lda : BK;      // elements per k-block
-    const int64_t b_kstep = p.b_mn_major ? (int64_t)BK * p.ldb : BK;
-    int w = blockIdx.x, kb = 0, nkb = 0, mt = 0, nt = 0, kbeg = 0;
-    auto setup = [&]() {
-      if (w >= nwork) { nkb = 0; return; }
-      nt = w % p.tiles_n;
-      const int q = w / p.tiles_n;
-      mt = q % p.tiles_m;
-      kbeg = (q / p.tiles_m) * kb_per_split;
-      const int rem = kb_total - kbeg;
-      nkb = rem < kb_per_split ? rem : kb_per_split;
-      kb = 0;
-    };
-    auto advance = [&]() {
-      if (++kb >= nkb) { w += gridDim.x; setup(); }
-    };
-    setup();
-    int j = 0;                                            // index in the CTA's k-block sequence
-    for (int g = 0; g < group && w < nwork; ++g) { advance(); ++j; }
-    while (w < nwork) {
-      const int64_t m0 = (int64_t)mt * BM, n0 = (int64_t)nt * BN;
-      const int64_t k0 = (int64_t)(kbeg + kb) * BK;
-      const int64_t klim = (int64_t)(kbeg + nkb) * BK < p.K ? (int64_t)(kbeg + nkb) * BK : p.K;
-      float4 r[8];
-      if (p.a_vec && p.b_vec && m0 + BM <= p.M && n0 + BN <= p.N && k0 + BK <= klim) {
-        const float* pa = p.A + (p.a_mn_major ? m0 : m0 * p.lda) + (int64_t)(kbeg + kb) * a_kstep + ga0;
-        const float* pb = p.B + (p.b_mn_major ? n0 : n0 * p.ldb) + (int64_t)(kbeg + kb) * b_kstep + gb0;
+  if (warp == TMA_WARP) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int nt = (int)(w % p.tiles_n);
+        const int mt = (int)((w / p.tiles_n) % p.tiles_m);
+        const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int64_t kbeg = (int64_t)ks * p.k_per_split;
+        const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
+        for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&raw_bar[stage], (p.b_presplit ? 3 : 2) * TILE_BYTES);
+          if (!p.a_mn_major) {
+            tma_load_2d(st, &tmA, (int)k0, m0, &raw_bar[stage]);
+          } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          r[i] = __ldg(reinterpret_cast<const float4*>(pa + i * gas));
-          r[4 + i] = __ldg(reinterpret_cast<const float4*>(pb + i * gbs));
-        }
-      } else {             // edge tiles: guarded element-wise loads with zero fill
+            for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &tmA, m0 + 32 * b, (int)k0, &raw_bar[stage]);
+          }
+          if (!p.b_mn_major) {
+            tma_load_2d(st + 2 * TILE_BYTES, &tmB, (int)k0, n0, &raw_bar[stage]);
+            if (p.b_presplit) tma_load_2d(st + 3 * TILE_BYTES, &tmB2, (int)k0, n0, &raw_bar[stage]);
+          } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (!p.a_mn_major) r[i] = load4(p.A, m0 + (pt >> 3) + 32 * i, p.lda, k0 + (pt & 7) * 4, p.M, klim, p.a_vec);
-          else r[i] = load4(p.A, k0 + (pt >> 5) + 8 * i, p.lda, m0 + (pt & 31) * 4, klim, p.M, p.a_vec);
-          if (!p.b_mn_major) r[4 + i] = load4(p.B, n0 + (pt >> 3) + 32 * i, p.ldb, k0 + (pt & 7) * 4, p.N, klim, p.b_vec);
-          else r[4 + i] = load4(p.B, k0 + (pt >> 5) + 8 * i, p.ldb, n0 + (pt & 31) * 4, klim, p.N, p.b_vec);
+            for (int b = 0; b < 4; ++b) tma_load_2d(st + 2 * TILE_BYTES + b * 4096, &tmB, n0 + 32 * b, (int)k0, &raw_bar[stage]);
+            if (p.b_presplit) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) tma_load_2d(st + 3 * TILE_BYTES + b * 4096, &tmB2, n0 + 32 * b, (int)k0, &raw_bar[stage]);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      const int stage = j % STAGES;
-      mbar_wait(&empty_bar[stage], ((j / STAGES) & 1) ^ 1);
-      char* st = reinterpret_cast<char*>(smem) + (size_t)stage * STAGE_BYTES;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        split_store(st, st + TILE_BYTES, sa0 + i * sas, r[i]);
-        split_store(st, st + TILE_BYTES, sb0 + i * sbs, r[4 + i]);
+    }
+  } else if (warp >= SPLIT_WARP0) {
+    // ============================== hi/lo split (smem -> smem) ==============================
+    const int tt = threadIdx.x - SPLIT_WARP0 * 32;           // 0..255
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
+      const int64_t kbeg = (int64_t)ks * p.k_per_split;
+      const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
+      for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+        mbar_wait(&raw_bar[stage], phase);                   // TMA bytes have landed
+        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+        const int nchunk = p.b_presplit ? 1024 / SPLIT_THREADS : 2048 / SPLIT_THREADS;
+#pragma unroll 4
+        for (int i = 0; i < nchunk; ++i) {
+          const int chunk = tt + SPLIT_THREADS * i;          // [0,1024): A tile, [1024,2048): B tile
+          uint8_t* hi = st + (chunk >> 10) * (2 * TILE_BYTES) + (chunk & 1023) * 16;
+          const float4 v = *reinterpret_cast<const float4*>(hi);
+          float4 h, l;
+          h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+          l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+          *reinterpret_cast<float4*>(hi) = h;
+          *reinterpret_cast<float4*>(hi + TILE_BYTES) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
-      // skip the other groups' k-blocks
-      for (int g = 0; g < PROD_GROUPS && w < nwork; ++g) advance();
-      j += PROD_GROUPS;
     }
   } else if (warp == MMA_WARP) {
     // ============================== MMA issuer ==============================
@@ -385,7 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const Params p) {
   }
 }
 
-__global__ void tc_splitk_reduce(const float* __restrict__ partial, int parts, int64_t M, int64_t N,
+__global__ void tma_splitk_reduce(const float* __restrict__ partial, int parts, int64_t M, int64_t N,
                                  const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
@@ -419,33 +377,90 @@ Plan make_plan(int64_t M, int64_t N, int64_t K) {
   return pl;
 }
 
+
+
+// weights: hi = rn_tf32(w), lo = rn_tf32(w - hi), same [rows, ld] layout, done once per call (tiny)
+__global__ void presplit_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ hi,
+                                float* __restrict__ lo, int64_t ldo) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols, c = i - r * cols;
+  const float x = w[r * ld + c];
+  const float h = tf32_rn(x);
+  hi[r * ldo + c] = h;
+  lo[r * ldo + c] = tf32_rn(x - h);
+}
+
+constexpr int64_t PRESPLIT_MAX_ELEMS = 1 << 22;   // B operands up to 16 MB (weights) are pre-split
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  return fn;
+}
+
+// operand stored [rows, cols] row-major with leading dimension ld (floats).  K-major use: cols = K, box 32 x 128,
+// SWIZZLE_128B.  MN-major use: cols = M or N, rows = K, box 32 x 32, SWIZZLE_128B_ATOM_32B.
+bool make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld, bool mn_major) {
+  EncodeFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, mn_major ? 32u : 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace
 
-bool tagan_gemm_tc_supported(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
-                             int64_t ldb) {
-  (void)op; (void)M; (void)N; (void)A; (void)B; (void)lda; (void)ldb;
-  return K > 0;
+bool tagan_gemm_tma_supported(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb) {
+  if (K <= 0 || M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31)) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 4) || (ldb % 4)) return false;
+  return get_encode() != nullptr;
 }
 
-size_t tagan_gemm_tc_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K) {
-  (void)op;
+static inline int64_t presplit_ld(int64_t cols) { return (cols + 3) / 4 * 4; }
+static inline bool want_presplit(int32_t op, int64_t N, int64_t K) { return op != 2 && N * K <= PRESPLIT_MAX_ELEMS; }
+
+size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K) {
   Plan pl = make_plan(M, N, K);
-  return pl.splits > 1 ? (size_t)pl.splits * (size_t)M * (size_t)N * sizeof(float) : 0;
+  size_t b = pl.splits > 1 ? (size_t)pl.splits * (size_t)M * (size_t)N * sizeof(float) : 0;
+  if (want_presplit(op, N, K)) {
+    const int64_t rows = op == 0 ? N : K, cols = op == 0 ? K : N;
+    b = (b + 255) / 256 * 256 + 2 * (size_t)rows * presplit_ld(cols) * sizeof(float) + 256;
+  }
+  return b;
 }
 
-int tagan_gemm_tc(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
-                  int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
-                  void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                   int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   Plan pl = make_plan(M, N, K);
   Params p;
   p.M = M; p.N = N; p.K = K;
-  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.bias = bias; p.C = C; p.ldc = ldc;
+  p.bias = bias; p.C = C; p.ldc = ldc;
   p.accumulate = accumulate;
   p.passes = passes;
   p.a_mn_major = (op == 2);
@@ -456,19 +471,33 @@ int tagan_gemm_tc(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, i
     if (!workspace || workspace_bytes < (size_t)pl.splits * M * N * sizeof(float)) return TAGAN_E_WORKSPACE;
     p.partial = static_cast<float*>(workspace);
   }
-  p.a_vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 4 == 0);
-  p.b_vec = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0);
   if (p.partial) p.c_vec = (N % 4 == 0);
-  else p.c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0) &&
-                 (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
-  // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13),
-  // a_major [15], b_major [16] (1 = MN-major), n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
+  else p.c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0);
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) | ((uint32_t)p.b_mn_major << 16) |
             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  CUtensorMap tmA, tmB, tmB2;
+  // NT: A[M,K], B[N,K] (K-major).  NN: A[M,K], B[K,N] (MN-major).  TN: A[K,M], B[K,N] (both MN-major).
+  const bool okA = p.a_mn_major ? make_map(&tmA, A, K, M, lda, true) : make_map(&tmA, A, M, K, lda, false);
+  p.b_presplit = 0;
+  bool okB;
+  if (want_presplit(op, N, K) && passes != 1) {
+    const int64_t rows = op == 0 ? N : K, cols = op == 0 ? K : N, ldo = presplit_ld(cols);
+    size_t off = pl.splits > 1 ? ((size_t)pl.splits * M * N * sizeof(float) + 255) / 256 * 256 : 0;
+    if (!workspace || workspace_bytes < off + 2 * (size_t)rows * ldo * sizeof(float)) return TAGAN_E_WORKSPACE;
+    float* hi = reinterpret_cast<float*>(static_cast<char*>(workspace) + off);
+    float* lo = hi + rows * ldo;
+    presplit_kernel<<<ceil_div_i64(rows * cols, 256), 256, 0, st>>>(B, rows, cols, ldb, hi, lo, ldo);
+    okB = make_map(&tmB, hi, rows, cols, ldo, p.b_mn_major) && make_map(&tmB2, lo, rows, cols, ldo, p.b_mn_major);
+    p.b_presplit = 1;
+  } else {
+    okB = p.b_mn_major ? make_map(&tmB, B, K, N, ldb, true) : make_map(&tmB, B, N, K, ldb, false);
+    tmB2 = tmB;
+  }
+  if (!okA || !okB) return TAGAN_E_UNSUPPORTED;
   int64_t work = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits;
   int grid = (int)(work < 148 ? work : 148);
-  gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  gemm_tma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2);
   if (p.partial)
-    tc_splitk_reduce<<<ceil_div_i64(M * N, 256), 256, 0, st>>>(p.partial, pl.splits, M, N, bias, C, ldc, accumulate);
+    tma_splitk_reduce<<<ceil_div_i64(M * N, 256), 256, 0, st>>>(p.partial, pl.splits, M, N, bias, C, ldc, accumulate);
   return tagan_launch_status();
 }

@@ -35,10 +35,11 @@ def _ref(op, a, b, bias):
     return r
 
 
+@pytest.mark.parametrize("precision", [1, 3, 5])  # 1/3 = TMA-fed kernel (3 / 4 MMAs per k-step), 5 = LDG-fed kernel
 @pytest.mark.parametrize("op", [0, 1, 2])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 32), (128, 128, 128), (256, 384, 128), (1000, 384, 128), (4096, 768, 256),
                                    (333, 200, 100), (130, 70, 36), (5000, 128, 512)])
-def test_gemm_tc_matches_fp64(op, m, n, k):
+def test_gemm_tc_matches_fp64(op, m, n, k, precision):
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(m + n + k + op)
     if op == 0:
@@ -51,7 +52,7 @@ def test_gemm_tc_matches_fp64(op, m, n, k):
     a, b = a.to(dev), b.to(dev)
     bias_d = bias.to(dev) if bias is not None else None
     ref = _ref(op, a.cpu(), b.cpu(), bias)
-    out = _gemm(op, a, b, bias_d, m, n, k, precision=1)
+    out = _gemm(op, a, b, bias_d, m, n, k, precision=precision)
     torch.cuda.synchronize()
     scale = float(ref.abs().max())
     torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-4, atol=1e-5 * max(1.0, scale))

@@ -47,7 +47,7 @@ def main():
     shapes = [(0, rows, 384, 128), (0, rows, 128, 128), (0, rows, 256, 256), (1, rows, 128, 384), (1, rows, 256, 128),
               (2, 384, 128, rows), (2, 128, 128, rows), (2, 256, 256, rows), (0, 100_000, 384, 128), (0, 1_000_000, 768, 256)]
     for op, m, n, k in shapes:
-        for prec in (0, 1, 2):
+        for prec in (1, 3, 2):
             print(json.dumps(run(op, m, n, k, prec)), flush=True)
 
 
