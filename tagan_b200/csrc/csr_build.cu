@@ -145,6 +145,10 @@ __global__ void scatter_edges(const int64_t* __restrict__ ei, int64_t E, int n, 
 // at the segment start (count -> ucount[seg]); otherwise a stable full sort with a payload.
 constexpr int SORT_SMEM_KEYS = 8192;
 
+// Segments of up to WARP_SEG entries: one warp, each lane holds two keys (positions lane and lane+32);
+// ranks are counted with register shuffles only.
+constexpr int WARP_SEG = 64;
+
 template <bool UNIQUE, bool PAYLOAD>
 __global__ void seg_sort_warp(const int* __restrict__ off, const int* __restrict__ kin, const int* __restrict__ pin,
                               int* __restrict__ kout, int* __restrict__ pout, int* __restrict__ ucount, int nseg) {
@@ -152,34 +156,51 @@ __global__ void seg_sort_warp(const int* __restrict__ off, const int* __restrict
   int lane = threadIdx.x & 31;
   if (seg >= nseg) return;
   int b = off[seg], len = off[seg + 1] - b;
-  if (len > 32) return;  // handled by seg_sort_block
-  int key = lane < len ? kin[b + lane] : 0x7fffffff;
-  int pay = 0;
-  if (PAYLOAD) pay = lane < len ? pin[b + lane] : 0;
+  if (len > WARP_SEG) return;  // handled by seg_sort_block
+  const int i0 = lane, i1 = lane + 32;
+  const int key0 = i0 < len ? kin[b + i0] : 0x7fffffff;
+  const int key1 = i1 < len ? kin[b + i1] : 0x7fffffff;
+  int pay0 = 0, pay1 = 0;
+  if (PAYLOAD) { pay0 = i0 < len ? pin[b + i0] : 0; pay1 = i1 < len ? pin[b + i1] : 0; }
+  const int lo_n = len < 32 ? len : 32, hi_n = len - lo_n;   // valid entries in the two halves
   if (UNIQUE) {
-    bool first = lane < len;
-    for (int j = 0; j < len; ++j) {
-      int kj = __shfl_sync(FULL_MASK, key, j);
-      if (kj == key && j < lane) first = false;
+    bool first0 = i0 < len, first1 = i1 < len;
+    for (int j = 0; j < lo_n; ++j) {
+      const int kj = __shfl_sync(FULL_MASK, key0, j);
+      if (kj == key0 && j < i0) first0 = false;
+      if (kj == key1) first1 = false;                          // every position of the low half precedes i1
     }
-    unsigned fm = __ballot_sync(FULL_MASK, first);
-    int urank = 0;
-    for (int j = 0; j < len; ++j) {
-      int kj = __shfl_sync(FULL_MASK, key, j);
-      if (((fm >> j) & 1u) && kj < key) ++urank;
+    for (int j = 0; j < hi_n; ++j) {
+      const int kj = __shfl_sync(FULL_MASK, key1, j);
+      if (kj == key1 && j + 32 < i1) first1 = false;
     }
-    if (first) kout[b + urank] = key;
-    if (lane == 0) ucount[seg] = __popc(fm);
+    const unsigned fm0 = __ballot_sync(FULL_MASK, first0), fm1 = __ballot_sync(FULL_MASK, first1);
+    int ur0 = 0, ur1 = 0;
+    for (int j = 0; j < lo_n; ++j) {
+      const int kj = __shfl_sync(FULL_MASK, key0, j);
+      if ((fm0 >> j) & 1u) { ur0 += kj < key0; ur1 += kj < key1; }
+    }
+    for (int j = 0; j < hi_n; ++j) {
+      const int kj = __shfl_sync(FULL_MASK, key1, j);
+      if ((fm1 >> j) & 1u) { ur0 += kj < key0; ur1 += kj < key1; }
+    }
+    if (first0) kout[b + ur0] = key0;
+    if (first1) kout[b + ur1] = key1;
+    if (lane == 0) ucount[seg] = __popc(fm0) + __popc(fm1);
   } else {
-    int rank = 0;
-    for (int j = 0; j < len; ++j) {
-      int kj = __shfl_sync(FULL_MASK, key, j);
-      if (kj < key || (kj == key && j < lane)) ++rank;
+    int r0 = 0, r1 = 0;
+    for (int j = 0; j < lo_n; ++j) {
+      const int kj = __shfl_sync(FULL_MASK, key0, j);
+      r0 += (kj < key0) || (kj == key0 && j < i0);
+      r1 += (kj <= key1);                                      // low-half positions precede i1: ties rank before
     }
-    if (lane < len) {
-      kout[b + rank] = key;
-      if (PAYLOAD) pout[b + rank] = pay;
+    for (int j = 0; j < hi_n; ++j) {
+      const int kj = __shfl_sync(FULL_MASK, key1, j);
+      r0 += (kj < key0);                                       // high-half positions follow i0: ties rank after
+      r1 += (kj < key1) || (kj == key1 && j + 32 < i1);
     }
+    if (i0 < len) { kout[b + r0] = key0; if (PAYLOAD) pout[b + r0] = pay0; }
+    if (i1 < len) { kout[b + r1] = key1; if (PAYLOAD) pout[b + r1] = pay1; }
   }
 }
 
@@ -188,9 +209,21 @@ __global__ void seg_sort_block(const int* __restrict__ off, const int* __restric
                                int* __restrict__ kout, int* __restrict__ pout, int* __restrict__ ucount, int nseg) {
   __shared__ int skey[SORT_SMEM_KEYS];
   __shared__ int scount;
-  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+  __shared__ int long_list[256];
+  __shared__ int long_count;
+  // find the long segments 256 at a time (one thread per segment), then sort each with the whole block
+  for (int base = blockIdx.x * 256; base < nseg; base += gridDim.x * 256) {
+   if (threadIdx.x == 0) long_count = 0;
+   __syncthreads();
+   {
+     const int sg = base + threadIdx.x;
+     if (sg < nseg && off[sg + 1] - off[sg] > WARP_SEG) long_list[atomicAdd(&long_count, 1)] = sg;
+   }
+   __syncthreads();
+   const int nlong = long_count;
+   for (int li = 0; li < nlong; ++li) {
+    const int seg = long_list[li];
     int b = off[seg], len = off[seg + 1] - b;
-    if (len <= 32) continue;
     const bool in_smem = len <= SORT_SMEM_KEYS;
     __syncthreads();
     if (in_smem)
@@ -234,6 +267,8 @@ __global__ void seg_sort_block(const int* __restrict__ off, const int* __restric
       __syncthreads();
       if (threadIdx.x == 0) ucount[seg] = scount;
     }
+   }
+   __syncthreads();
   }
 }
 

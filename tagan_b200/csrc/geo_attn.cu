@@ -131,6 +131,9 @@ __device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const float*
 // warp-per-row kernels skip them and a second launch gives each of them a whole CTA -- its 8 warps take
 // contiguous slices of the entries and their partial states are merged through shared memory in warp
 // order, so the result stays deterministic and independent of scheduling (power-law graphs, config 2).
+// resident CTAs per SM the register allocator must allow: memory-level parallelism is the limiter of these
+// gather kernels (profiles/r01_SUMMARY.md), so occupancy is worth a few spilled scalars
+constexpr int min_ctas(int vec, int nchunk) { return vec * nchunk >= 16 ? 2 : (vec * nchunk >= 8 ? 3 : 4); }
 constexpr int HEAVY_THRESH = 128;
 constexpr int HEAVY_GRID = 148 * 2;
 
@@ -245,7 +248,7 @@ __device__ __forceinline__ void fwd_attn_pass(const RowCtx<METRIC, VEC, NCHUNK>&
 }
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas(VEC, NCHUNK))
 geo_attn_fwd_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                     const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
                     const float* __restrict__ metric_param, float* __restrict__ ctx, float* __restrict__ lse,
@@ -380,7 +383,7 @@ __device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& 
 }
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas(VEC, NCHUNK))
 geo_attn_bwd_row_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                         const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
                         const float* __restrict__ metric_param, const float* __restrict__ ctx,
@@ -531,7 +534,7 @@ __device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], cons
 }
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas(VEC, NCHUNK))
 geo_attn_bwd_col_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                         const int* __restrict__ rowptr_t, const int* __restrict__ row_t, int N, int heads, int D,
                         const float* __restrict__ metric_param, const float* __restrict__ lse,
