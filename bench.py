@@ -275,10 +275,38 @@ def run_ours(args):
     if not args.no_e2e:
         h2d = sum(x.numel() * 4 for x in xs_h) + sum(ei.numel() * 8 for ei in eis_h)
 
+        copy_stream = torch.cuda.Stream(device=dev)
+
         def e2e_step():
-            xs = [x.to(dev, non_blocking=True) for x in xs_h]
-            eis = [ei.to(dev, non_blocking=True) for ei in eis_h]
-            return float(step(xs, eis).item())
+            # per-snapshot H2D copies run on a copy stream; the compute stream waits for snapshot t only when the
+            # geometric layer reaches it, so the 1.3 GB of input copies overlap with the kernels of earlier snapshots
+            main = torch.cuda.current_stream()
+            copy_stream.wait_stream(main)
+            xs, eis, evs = [], [], []
+            with torch.cuda.stream(copy_stream):
+                for x, ei in zip(xs_h, eis_h):
+                    xs.append(x.to(dev, non_blocking=True))
+                    eis.append(ei.to(dev, non_blocking=True))
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    evs.append(ev)
+            for x, ei in zip(xs, eis):
+                x.record_stream(main)
+                ei.record_stream(main)
+
+            class _Lazy:
+                """list whose items make the compute stream wait for their copy on first access"""
+                def __init__(self, items):
+                    self.items = items
+
+                def __iter__(self):
+                    for t, it in enumerate(self.items):
+                        main.wait_event(evs[t])
+                        yield it
+
+                def __len__(self):
+                    return len(self.items)
+            return float(step(_Lazy(xs), _Lazy(eis)).item())
         e2e_step()
         barrier()
         t0 = time.perf_counter()

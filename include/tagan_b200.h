@@ -189,7 +189,7 @@ int tagan_gemm(int32_t op /*0=NT,1=NN,2=TN*/, int64_t m, int64_t n, int64_t k,
  * ------------------------------------------------------------------------------------- */
 int tagan_tattn_fwd(const float* Q, const float* K, const float* V, int64_t ld,
                     int64_t batch, int32_t T, int32_t hidden, int32_t heads, int32_t time_major,
-                    const float* bias_t, int64_t bias_bstride, const float* ts,
+                    const float* bias, const float* bias_t, int64_t bias_bstride, const float* ts,
                     int32_t mask_flags, float band, const int32_t* allones_flag,
                     const uint8_t* mask, int32_t mask_b, int32_t mask_h,
                     float* ctx, float* lse, float* attn, tagan_stream_t stream);

@@ -21,51 +21,9 @@
 // row) recomputes the probabilities and gives dK, dV.  dBias for a shared table is reduced over
 // nodes through per-CTA partial tables summed in a fixed order.
 #include "common.cuh"
+#include "temporal_attn_shared.cuh"
 
 namespace {
-
-constexpr int MAX_WARPS = 8;
-constexpr int SMEM_LIMIT = 200 * 1024;
-
-struct MaskSpec {
-  const float* ts;            // [B,T] or null
-  int flags;                  // bit0 causal, bit1 band, bit2 allones=>causal
-  float band;
-  const int* allones_flag;    // device
-  const uint8_t* mask;        // [mask_b, mask_h, T, T] keep-mask or null
-  int mask_b, mask_h;
-};
-
-__device__ __forceinline__ bool key_valid(const MaskSpec& ms, bool causal, const float* ts_s, const uint8_t* mrow_base,
-                                          int T, int i, int j) {
-  bool v = true;
-  if (causal) v = j <= i;
-  if ((ms.flags & 2) && ts_s) v = v && (fabsf(ts_s[i] - ts_s[j]) <= ms.band);
-  if (mrow_base) v = v && (mrow_base[(int64_t)i * T + j] != 0);
-  return v;
-}
-
-template <int D>
-__device__ __forceinline__ float dot_smem(const float* q, const float* ks) {
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < D; c += 4) {
-    float4 k4 = *reinterpret_cast<const float4*>(ks + c);
-    s = fmaf(q[c], k4.x, s); s = fmaf(q[c + 1], k4.y, s); s = fmaf(q[c + 2], k4.z, s); s = fmaf(q[c + 3], k4.w, s);
-  }
-  return s;
-}
-
-// cooperative copy of a [T,D] head slice (row stride ld) into smem by `nl` lanes starting at lane id `li`
-template <int D>
-__device__ __forceinline__ void load_tile(float* dst, const float* src, int64_t ld, int T, int li, int nl) {
-  constexpr int C4 = D / 4;
-  for (int idx = li; idx < T * C4; idx += nl) {
-    int t = idx / C4, c = idx - t * C4;
-    float4 v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)t * ld + c * 4));
-    *reinterpret_cast<float4*>(dst + t * D + c * 4) = v;
-  }
-}
 
 // ---------------------------------------------------------------------------------------
 // forward
@@ -320,6 +278,7 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
   }
 }
 
+
 __global__ void reduce_parts(const float* __restrict__ partial, int parts, int64_t n, float* __restrict__ out) {
   int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= n) return;
@@ -396,7 +355,8 @@ int bwd_grid(int64_t B) { return (int)(B < 148 * 4 ? B : 148 * 4); }
 }  // namespace
 
 TAGAN_API int tagan_tattn_fwd(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
-                              int32_t H, int32_t heads, int32_t time_major, const float* bias_t, int64_t bias_bstride, const float* ts,
+                              int32_t H, int32_t heads, int32_t time_major, const float* bias, const float* bias_t,
+                              int64_t bias_bstride, const float* ts,
                               int32_t mask_flags, float band, const int32_t* allones_flag, const uint8_t* mask,
                               int32_t mask_b, int32_t mask_h, float* ctx, float* lse, float* attn,
                               tagan_stream_t stream) {
@@ -421,6 +381,11 @@ TAGAN_API int tagan_tattn_fwd(const float* Q, const float* K, const float* V, in
     default: rc = set_smem(tattn_fwd_kernel<64>, c.smem); break;
   }
   if (rc) return rc;
+  const bool fast = T <= 32 && c.warps * c.PPW >= heads && bias_bstride == 0 && c.smem <= 48 * 1024 &&
+                    (bias == nullptr) == (bias_t == nullptr);
+  if (fast && tagan_tattn_fwd_fast_launch(D, c.TP, grid, c.warps * 32, c.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
+                                          ctx, lse, attn))
+    return tagan_launch_status();
   DISPATCH_D(tattn_fwd_kernel, <<<grid, c.warps * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias_t, bias_bstride, ms, ctx, lse, attn, c.TP, c.warps))
   return tagan_launch_status();
 }
@@ -470,7 +435,12 @@ TAGAN_API int tagan_tattn_bwd(const float* Q, const float* K, const float* V, in
     default: rc = set_smem(tattn_bwd_kernel<64>, c.smem); break;
   }
   if (rc) return rc;
-  DISPATCH_D(tattn_bwd_kernel, <<<grid, c.warps * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, bias_t, bias_bstride, ms, ctx, lse, dctx, dQ, dK, dV, ldd, db_target, per_node ? 1 : 0, c.TP, c.warps))
+  const bool fast = T <= 32 && c.warps * c.PPW >= heads && !per_node && c.smem <= 48 * 1024;
+  if (fast && tagan_tattn_bwd_fast_launch(D, c.TP, grid, c.warps * 32, c.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
+                                          ctx, lse, dctx, dQ, dK, dV, ldd, db_target)) {
+  } else {
+    DISPATCH_D(tattn_bwd_kernel, <<<grid, c.warps * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, bias_t, bias_bstride, ms, ctx, lse, dctx, dQ, dK, dV, ldd, db_target, per_node ? 1 : 0, c.TP, c.warps))
+  }
   if (dbias && !per_node) {
     const int64_t n = (int64_t)heads * T * T;
     reduce_parts<<<ceil_div_i64(n, 256), 256, 0, st>>>(db_target, grid, n, dbias);

@@ -1,0 +1,61 @@
+// Pieces shared by temporal_attn.cu (generic kernels + C ABI) and temporal_attn_fast.cu (T <= 32 fast path).
+#pragma once
+#include "common.cuh"
+
+namespace tagan_tattn {
+
+constexpr int MAX_WARPS = 8;
+constexpr int SMEM_LIMIT = 200 * 1024;
+
+struct MaskSpec {
+  const float* ts;            // [B,T] or null
+  int flags;                  // bit0 causal, bit1 band, bit2 allones=>causal
+  float band;
+  const int* allones_flag;    // device
+  const uint8_t* mask;        // [mask_b, mask_h, T, T] keep-mask or null
+  int mask_b, mask_h;
+};
+
+__device__ __forceinline__ bool key_valid(const MaskSpec& ms, bool causal, const float* ts_s, const uint8_t* mrow_base,
+                                          int T, int i, int j) {
+  bool v = true;
+  if (causal) v = j <= i;
+  if ((ms.flags & 2) && ts_s) v = v && (fabsf(ts_s[i] - ts_s[j]) <= ms.band);
+  if (mrow_base) v = v && (mrow_base[(int64_t)i * T + j] != 0);
+  return v;
+}
+
+template <int D>
+__device__ __forceinline__ float dot_smem(const float* q, const float* ks) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < D; c += 4) {
+    float4 k4 = *reinterpret_cast<const float4*>(ks + c);
+    s = fmaf(q[c], k4.x, s); s = fmaf(q[c + 1], k4.y, s); s = fmaf(q[c + 2], k4.z, s); s = fmaf(q[c + 3], k4.w, s);
+  }
+  return s;
+}
+
+// cooperative copy of a [T,D] head slice (row stride ld) into smem by `nl` lanes starting at lane id `li`
+template <int D>
+__device__ __forceinline__ void load_tile(float* dst, const float* src, int64_t ld, int T, int li, int nl) {
+  constexpr int C4 = D / 4;
+  for (int idx = li; idx < T * C4; idx += nl) {
+    int t = idx / C4, c = idx - t * C4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)t * ld + c * 4));
+    *reinterpret_cast<float4*>(dst + t * D + c * 4) = v;
+  }
+}
+
+
+}  // namespace tagan_tattn
+using namespace tagan_tattn;
+
+// fast-path launchers (temporal_attn_fast.cu); return false when (D, TP) is not instantiated
+bool tagan_tattn_fwd_fast_launch(int D, int TP, int grid, int threads, size_t smem, cudaStream_t st, const float* Q,
+                                 const float* K, const float* V, int64_t ld, int64_t B, int T, int heads, int64_t rsb,
+                                 int64_t rst, const float* bias, MaskSpec ms, float* ctx, float* lse, float* attn);
+bool tagan_tattn_bwd_fast_launch(int D, int TP, int grid, int threads, size_t smem, cudaStream_t st, const float* Q,
+                                 const float* K, const float* V, int64_t ld, int64_t B, int T, int heads, int64_t rsb,
+                                 int64_t rst, const float* bias, MaskSpec ms, const float* ctx, const float* lse,
+                                 const float* dctx, float* dQ, float* dK, float* dV, int64_t ldd, float* dbias_partial);

@@ -424,7 +424,7 @@ class _TAttnFn(torch.autograd.Function):
         base = qkv2.data_ptr()
         q, k, v = (C.c_void_p(base + i * h * 4) for i in range(3))
         with _timed("tattn_fwd"):
-            rc = lib.tagan_tattn_fwd(q, k, v, ld, batch, t, h, heads, int(time_major), _ptr(bias_t), bstride,
+            rc = lib.tagan_tattn_fwd(q, k, v, ld, batch, t, h, heads, int(time_major), _ptr(bias_c), _ptr(bias_t), bstride,
                                      _ptr(tmask.ts), tmask.flags, tmask.band, _ptr(tmask.allones_flag), _ptr(m), mb, mh,
                                      _ptr(ctxv), _ptr(lse), _ptr(attn), _stream())
         _lib.check(rc, "tagan_tattn_fwd")
