@@ -6,7 +6,7 @@ workloads (``synth``).  The package name is ``tagan_b200`` because the repositor
 (``temporal-asymmetric-graph-attention-network_b200``) is not an importable identifier.
 """
 from . import _lib, ops  # noqa: F401
-from .layers import (AsymmetricTemporalAttention, GeometricAttention, TAGANGraphAttention,  # noqa: F401
+from .layers import (AsymmetricTemporalAttention, GeometricAttention, LayerNorm, TAGANGraphAttention,  # noqa: F401
                      TemporalEvolutionLayer, TemporalGatingUnit, TemporalGRUCell, TemporalPropagation,
                      TemporalSkipConnection, TimeEncoding)
 

@@ -15,6 +15,14 @@ import torch.nn.functional as F
 from . import ops
 
 
+class LayerNorm(nn.LayerNorm):
+    """``nn.LayerNorm`` (same parameters / state_dict keys) whose forward runs ``tagan_layernorm_fwd``.
+    ``patch()`` uses it for the model-level ``skip_layer_norm`` (reference model.py:258-262, row a5)."""
+
+    def forward(self, x):
+        return ops.layer_norm(x, self.weight, self.bias)
+
+
 class GeometricAttention(nn.Module):
     """Mirror of reference ``GeometricAttention`` (src/tagan/layers/geometric_attention.py:228-598)
     operating on a CSR instead of a dense ``[1,N,N]`` mask."""
@@ -583,6 +591,44 @@ class TemporalPropagation(nn.Module):
         g, b = _ln_args(self, "layer_norm", self.use_layer_norm)
         return ops.layer_norm(o, g, b).view(t_steps, n, self.hidden_dim)
 
+    def forward_with_memory(self, xs, node_ids_seq, memory_bank, time_stamps: Optional[torch.Tensor] = None):
+        """The memory-bank gating pass the reference *intends* (temporal_propagation.py:1357-1485) but never
+        completes, as ONE vectorised pass per snapshot instead of a Python
+        loop over nodes:
+
+          prev, known = bank.get_states(ids_t)       (zeros for unknown ids, as get_states does :187-211)
+          gated       = gating_unit(evolved_t, prev)  for ids that had a stored state (:1417-1455);
+                        new ids keep their evolved features
+          bank.update(ids_t, gated.detach() + 0.01*t, t)   once per snapshot (:1463-1473)
+
+        Documented semantic choices (they cannot be parity-checked against the model, only against
+        ``NodeMemoryBank`` and ``TemporalGatingUnit`` individually): the whole-bank decay/prune runs once per
+        snapshot rather than once per node, and the ``memory_bias`` keyword the reference passes (which its gating
+        unit does not accept) is dropped.  xs: list of ``[N_t,H]``; node_ids_seq: list of int32 id tensors.
+        Returns ``[T,N,H]`` for equal-sized snapshots."""
+        x3 = torch.stack(list(xs), 0) if isinstance(xs, (list, tuple)) else xs
+        e = self.evolution_layer.forward_stacked(x3, time_stamps)
+        if self.use_skip_connection:
+            e = self.skip_connection.forward_stacked(e)
+        outs = []
+        for t in range(e.shape[0]):
+            ids = node_ids_seq[t]
+            ids_d = ids.to(e.device, dtype=torch.int32) if isinstance(ids, torch.Tensor) else ids
+            known = memory_bank.known_mask(ids_d)                      # before get_states inserts the unknown ids
+            prev = memory_bank.get_states(ids_d)
+            cur = e[t]
+            if self.use_gating:
+                gated = self.gating_unit(cur, prev)
+                cur = torch.where(known.unsqueeze(1), gated, cur)
+            memory_bank.update(ids_d, cur.detach() + (0.01 * t if t > 0 else 0.0), t)
+            outs.append(cur)
+        e = torch.stack(outs, 0)
+        t_steps, n, _ = e.shape
+        o = ops.linear(e.reshape(t_steps * n, -1), self.output_proj.weight, self.output_proj.bias)
+        o = self.dropout_layer(o)
+        g, b = _ln_args(self, "layer_norm", self.use_layer_norm)
+        return ops.layer_norm(o, g, b).view(t_steps, n, self.hidden_dim)
+
     def forward(self, node_features_seq, node_masks_seq=None, time_stamps=None, memory_bank=None):
         ids_given = (isinstance(node_masks_seq, list) and len(node_masks_seq) > 0
                      and not isinstance(node_masks_seq[0], torch.Tensor))
@@ -592,5 +638,8 @@ class TemporalPropagation(nn.Module):
             raise TypeError("object of type 'NodeMemoryBank' has no len()")
         if isinstance(node_features_seq, torch.Tensor):
             node_features_seq = [node_features_seq]
-        out = self.forward_core(node_features_seq, time_stamps)
+        if ids_given and memory_bank is not None and hasattr(memory_bank, "known_mask"):
+            out = self.forward_with_memory(node_features_seq, node_masks_seq, memory_bank, time_stamps)
+        else:
+            out = self.forward_core(node_features_seq, time_stamps)
         return list(out.unbind(0)), memory_bank

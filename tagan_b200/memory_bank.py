@@ -151,6 +151,11 @@ class NodeMemoryBank:
         CALLS["n"] += 2
         return out
 
+    def known_mask(self, node_ids) -> torch.Tensor:
+        """bool [M]: which ids currently have a stored state (``node_id in node_states``), on device."""
+        ids = self._slots(node_ids).long()
+        return self.valid[ids].bool()
+
     def get_state(self, node_id) -> Optional[torch.Tensor]:
         s = self._slot_of_key(node_id)
         if s is None or not bool(self.valid[s].item()):

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import AsymmetricTemporalAttention, TAGANGraphAttention, TemporalPropagation
+from .layers import AsymmetricTemporalAttention, LayerNorm, TAGANGraphAttention, TemporalPropagation
 from .memory_bank import NodeMemoryBank
 
 
@@ -26,12 +26,20 @@ class TAGANLayer(nn.Module):
         self.propagation = TemporalPropagation(hidden_dim, hidden_dim, dropout, window_size=temporal_window_size)
         self.temporal_attention = AsymmetricTemporalAttention(hidden_dim, num_heads, dropout, causal=causal_attention,
                                                               asymmetric_window_size=window_size)
+        # False: the reference's observable behaviour (bank gathered/updated, gating unit unused); True: the intended
+        # per-snapshot gating pass (TemporalPropagation.forward_with_memory)
+        self.gated_memory = False
 
     def forward(self, xs: Sequence[torch.Tensor], edge_indices: Sequence, time_stamps: Optional[torch.Tensor] = None,
                 bank: Optional[NodeMemoryBank] = None, node_ids: Optional[Sequence[torch.Tensor]] = None):
         """xs: T tensors ``[N,H]``; edge_indices: T ``[2,E]`` int64 tensors (or prebuilt ``ops.CSR``);
         time_stamps ``[N,T]``.  Returns ``[N,T,H]``."""
         geo = [self.geometric(x, ei) for x, ei in zip(xs, edge_indices)]
+        if bank is not None and self.gated_memory:
+            n = geo[0].shape[0]
+            ids_seq = node_ids if node_ids is not None else [torch.arange(n, dtype=torch.int32, device=geo[0].device)] * len(geo)
+            prop = self.propagation.forward_with_memory(geo, ids_seq, bank, time_stamps)
+            return self.temporal_attention(list(prop.unbind(0)), time_stamps=time_stamps)
         prop = self.propagation.forward_core(geo, time_stamps)                      # [T,N,H]
         if bank is not None:
             t_steps, n = prop.shape[0], prop.shape[1]
@@ -70,6 +78,10 @@ def patch(model: nn.Module) -> nn.Module:
                                      relative_position_bias=cfg.asymmetric_temporal_bias)
     ta.load_state_dict(model.temporal_attention.state_dict())
     model.temporal_attention = ta.to(dev)
+    if getattr(model, "skip_layer_norm", None) is not None:                          # row a5 (model.py:258-262)
+        ln = LayerNorm(cfg.hidden_dim)
+        ln.load_state_dict(model.skip_layer_norm.state_dict())
+        model.skip_layer_norm = ln.to(dev)
     if dev.type == "cuda":      # (on CPU only the module swap is done; the kernels need a CUDA device to run)
         model.memory_bank = NodeMemoryBank(cfg.hidden_dim, decay_factor=0.8, max_inactivity=cfg.temporal_window_size,
                                            device=dev)

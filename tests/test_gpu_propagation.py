@@ -186,3 +186,52 @@ def test_bidirectional_evolution_vs_torch_composition(dev):
         _close(a.grad.cpu(), b.grad.cpu())
     for k, p in ev.named_parameters():
         torch.testing.assert_close(p.grad.cpu(), gref[k].cpu(), **_gtol(gref[k].cpu()), msg=lambda m, k=k: f"d{k}: {m}")
+
+
+def test_forward_with_memory_vs_components(dev):
+    """Vectorised intended gating pass: checked step by step against the oracle components --
+    evolution/skip (oracle), gating unit (oracle), bank bookkeeping (numpy oracle, bit-exact)."""
+    import numpy as np
+    import tagan_b200
+    torch.manual_seed(11)
+    n, t, hidden = 60, 5, 32
+    tp = tagan_b200.TemporalPropagation(hidden, hidden, dropout=0.0, window_size=2).to(dev)
+    tp.strict_reference = False
+    xs = [torch.randn(n, hidden) for _ in range(t)]
+    ids_seq = [torch.randperm(100)[:n].int() for _ in range(t)]          # nodes come and go
+    bank = tagan_b200.NodeMemoryBank(hidden, 0.8, 2, device=dev, capacity=100)
+    out = tp.forward_with_memory([x.to(dev) for x in xs], [i.to(dev) for i in ids_seq], bank)
+    sd = {k: v.detach().cpu() for k, v in tp.state_dict().items()}
+    ev = R.evolution_layer(xs, None, R._sub(sd, "evolution_layer."))
+    ev = R.skip_connection(ev, R._sub(sd, "skip_connection."), 2, "mean")
+    ora = R.BankOracle(hidden, 100, 0.8, 2)
+    refs = []
+    for s in range(t):
+        ids = ids_seq[s].numpy()
+        known = torch.from_numpy(ora.valid[ids].astype(bool))
+        prev = torch.from_numpy(ora.get_states(ids))
+        gated = R.gating_unit(ev[s], prev, R._sub(sd, "gating_unit."))
+        cur = torch.where(known.unsqueeze(1), gated, ev[s])
+        ora.update(ids, (cur + (0.01 * s if s > 0 else 0.0)).numpy(), s)
+        refs.append(R._ln(R._lin(cur, sd, "output_proj"), sd, "layer_norm"))
+    _close(out.detach().cpu(), torch.stack(refs))
+    assert np.array_equal(bank.valid[:100].cpu().numpy().astype(bool), ora.valid.astype(bool))
+    assert np.array_equal(bank.inactivity[:100].cpu().numpy()[ora.valid.astype(bool)], ora.inactivity[ora.valid.astype(bool)])
+    v = ora.valid.astype(bool)
+    torch.testing.assert_close(bank.table[:100].cpu()[torch.from_numpy(v)], torch.from_numpy(ora.states[v]), rtol=1e-4, atol=1e-5)
+    # gradients flow to the gating unit and the GRU
+    out.sum().backward()
+    assert tp.gating_unit.update_gate.weight.grad is not None
+    assert float(tp.evolution_layer.forward_cell.candidate.weight.grad.abs().sum()) > 0
+
+
+def test_skip_layernorm_module_matches_torch(dev):
+    import tagan_b200
+    torch.manual_seed(2)
+    ln = tagan_b200.LayerNorm(128).to(dev)
+    with torch.no_grad():
+        ln.weight.add_(0.1 * torch.randn_like(ln.weight))
+        ln.bias.add_(0.1 * torch.randn_like(ln.bias))
+    x = torch.randn(500, 128, device=dev)
+    ref = torch.nn.functional.layer_norm(x, (128,), ln.weight, ln.bias, 1e-5)
+    _close(ln(x).detach(), ref.detach())
