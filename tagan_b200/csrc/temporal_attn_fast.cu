@@ -236,16 +236,16 @@ tattn_bwd_fast_kernel(const float* __restrict__ Q, const float* __restrict__ K, 
 
 // instantiated (D, TP) pairs: head dims 8/16/32 x padded lengths 8/16/32 (except 32x32, whose unrolled body is
 // too large to pay off); everything else takes the generic kernels
-#define FAST_CASES(FN, ARGS)                                   \
+#define FAST_CASES(FN, ...)                                    \
   switch (D * 64 + TP) {                                       \
-    case 8 * 64 + 8: FN<8, 8> ARGS; return true;               \
-    case 8 * 64 + 16: FN<8, 16> ARGS; return true;             \
-    case 8 * 64 + 32: FN<8, 32> ARGS; return true;             \
-    case 16 * 64 + 8: FN<16, 8> ARGS; return true;             \
-    case 16 * 64 + 16: FN<16, 16> ARGS; return true;           \
-    case 16 * 64 + 32: FN<16, 32> ARGS; return true;           \
-    case 32 * 64 + 8: FN<32, 8> ARGS; return true;             \
-    case 32 * 64 + 16: FN<32, 16> ARGS; return true;           \
+    case 8 * 64 + 8: FN<8, 8> __VA_ARGS__; return true;               \
+    case 8 * 64 + 16: FN<8, 16> __VA_ARGS__; return true;             \
+    case 8 * 64 + 32: FN<8, 32> __VA_ARGS__; return true;             \
+    case 16 * 64 + 8: FN<16, 8> __VA_ARGS__; return true;             \
+    case 16 * 64 + 16: FN<16, 16> __VA_ARGS__; return true;           \
+    case 16 * 64 + 32: FN<16, 32> __VA_ARGS__; return true;           \
+    case 32 * 64 + 8: FN<32, 8> __VA_ARGS__; return true;             \
+    case 32 * 64 + 16: FN<32, 16> __VA_ARGS__; return true;           \
     default: return false;                                     \
   }
 
