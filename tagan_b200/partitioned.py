@@ -53,48 +53,99 @@ def build_csr_part(edge_index: torch.Tensor, part: NodePartition, rank: int, tra
 
 
 class TorchDistComm:
-    """all_gather / reduce_scatter of equal-size blocks over a torch.distributed group (NCCL)."""
+    """all_gather / reduce_scatter of equal-size blocks over a torch.distributed group (NCCL).
+
+    Both collectives are started asynchronously (NCCL's own stream) and return a ``wait`` callable; the caller
+    decides when the compute stream has to wait, which is what lets the exchange of snapshot t+1 overlap the
+    kernels of snapshot t (forward) and the reduce-scatter of snapshot t overlap the backward of snapshot t-1."""
 
     def __init__(self, part: NodePartition, rank: int, group=None):
         self.part, self.rank, self.group = part, rank, group
         assert part.num_nodes % part.world == 0, "equal blocks required (pad the graph to a multiple of world)"
 
-    def all_gather_rows(self, local: torch.Tensor) -> torch.Tensor:
+    def all_gather_rows_async(self, local: torch.Tensor):
         out = torch.empty(self.part.num_nodes, local.shape[1], dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
-        return out
+        work = dist.all_gather_into_tensor(out, local.contiguous(), group=self.group, async_op=True)
+        return out, work.wait
 
-    def reduce_scatter_rows(self, full: torch.Tensor) -> torch.Tensor:
+    def reduce_scatter_rows_async(self, full: torch.Tensor):
         n_loc = self.part.num_nodes // self.part.world
         out = torch.empty(n_loc, full.shape[1], dtype=full.dtype, device=full.device)
-        dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group)
+        work = dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group, async_op=True)
+        return out, work.wait
+
+    def all_gather_rows(self, local):
+        out, wait = self.all_gather_rows_async(local)
+        wait()
         return out
+
+    def reduce_scatter_rows(self, full):
+        out, wait = self.reduce_scatter_rows_async(full)
+        wait()
+        return out
+
+
+def _async(comm, name, arg):
+    """Use the comm's async collective if it has one, else the blocking one with a no-op wait."""
+    fn = getattr(comm, name + "_async", None)
+    if fn is not None:
+        return fn(arg)
+    return getattr(comm, name)(arg), (lambda: None)
+
+
+class _Halo:
+    """Per-snapshot rendezvous between the gather node and the attention node of the autograd graph."""
+    __slots__ = ("gather_wait", "rs_out", "rs_wait", "dqkv")
+
+    def __init__(self):
+        self.gather_wait = self.rs_out = self.rs_wait = self.dqkv = None
+
+
+class _HaloGatherFn(torch.autograd.Function):
+    """forward: start the all-gather of this rank's K|V rows.  backward: wait for the reduce-scatter that the
+    attention node started, and hand back the complete dqkv = [dQ | dK|dV]."""
+
+    @staticmethod
+    def forward(ctx, qkv_loc, comm, halo: _Halo):
+        h = qkv_loc.shape[1] // 3
+        kv, halo.gather_wait = _async(comm, "all_gather_rows", qkv_loc.detach()[:, h:])
+        ctx.halo, ctx.h = halo, h
+        return kv
+
+    @staticmethod
+    def backward(ctx, _dkv_placeholder):
+        halo, h = ctx.halo, ctx.h
+        halo.rs_wait()
+        halo.dqkv[:, h:] = halo.rs_out
+        out = halo.dqkv
+        halo.dqkv = halo.rs_out = None
+        return out, None, None
 
 
 class _PartGeoAttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv_loc, metric_param, csr: CSR, comm, heads: int, metric: int, n_src: int):
+    def forward(ctx, qkv_loc, kv, metric_param, csr: CSR, comm, halo: _Halo, heads: int, metric: int, n_src: int):
         lib = _lib.load()
         qkv2 = _f32c(qkv_loc).contiguous()
         n_loc, three_h = qkv2.shape
         h = three_h // 3
-        kv = comm.all_gather_rows(qkv2[:, h:])                       # [N, 2H]  (the halo exchange)
+        halo.gather_wait()                                           # compute stream waits for the halo only now
         ctxv = torch.empty(n_loc, h, dtype=torch.float32, device=qkv2.device)
         lse = torch.empty(n_loc, heads, dtype=torch.float32, device=qkv2.device)
         k_ptr, v_ptr = C.c_void_p(kv.data_ptr()), C.c_void_p(kv.data_ptr() + h * 4)
         rc = lib.tagan_geo_attn_fwd_part(_ptr(qkv2), three_h, k_ptr, v_ptr, 2 * h, _ptr(csr.rowptr), _ptr(csr.col), n_loc,
                                          h, heads, metric, _ptr(metric_param), _ptr(ctxv), _ptr(lse), None, _stream())
         _lib.check(rc, "tagan_geo_attn_fwd_part")
-        CALLS["n"] += 1
+        CALLS["n"] += 2
         ctx.save_for_backward(qkv2, kv, metric_param, ctxv, lse)
-        ctx.csr, ctx.comm, ctx.heads, ctx.metric, ctx.n_src = csr, comm, heads, metric, n_src
+        ctx.csr, ctx.comm, ctx.halo, ctx.heads, ctx.metric, ctx.n_src = csr, comm, halo, heads, metric, n_src
         return ctxv
 
     @staticmethod
     def backward(ctx, dctx):
         lib = _lib.load()
         qkv2, kv, metric_param, ctxv, lse = ctx.saved_tensors
-        csr, comm, heads, metric, n_src = ctx.csr, ctx.comm, ctx.heads, ctx.metric, ctx.n_src
+        csr, comm, halo, heads, metric, n_src = ctx.csr, ctx.comm, ctx.halo, ctx.heads, ctx.metric, ctx.n_src
         n_loc, three_h = qkv2.shape
         h = three_h // 3
         dev = qkv2.device
@@ -112,26 +163,62 @@ class _PartGeoAttnFn(torch.autograd.Function):
                                          _ptr(metric_param), _ptr(ctxv), _ptr(lse), _ptr(dctx), _ptr(dqkv), three_h,
                                          dk_ptr, dv_ptr, 2 * h, _ptr(delta), _ptr(dp_ws), _ptr(dparam), _stream())
         _lib.check(rc, "tagan_geo_attn_bwd_part")
-        CALLS["n"] += 2
-        dqkv[:, h:] = comm.reduce_scatter_rows(dkv_part)             # sum of every rank's partial dK|dV
-        return dqkv, dparam, None, None, None, None, None
+        CALLS["n"] += 4
+        # every rank's partial dK|dV -> owner; started now, awaited in _HaloGatherFn.backward
+        halo.rs_out, halo.rs_wait = _async(comm, "reduce_scatter_rows", dkv_part)
+        halo.dqkv = dqkv
+        return None, dkv_part, dparam, None, None, None, None, None, None
 
 
 def geo_attention_core_part(qkv_loc, csr: CSR, comm, heads: int, metric: str, n_src: int, metric_param=None):
-    return _PartGeoAttnFn.apply(qkv_loc, metric_param, csr, comm, heads, ops.METRIC_ID[metric], n_src)
+    halo = _Halo()
+    kv = _HaloGatherFn.apply(qkv_loc, comm, halo)
+    return _PartGeoAttnFn.apply(qkv_loc, kv, metric_param, csr, comm, halo, heads, ops.METRIC_ID[metric], n_src)
+
+
+def _project(layer, x_loc):
+    ln = layer.use_layer_norm
+    xn = ops.layer_norm(x_loc, layer.layer_norm1.weight, layer.layer_norm1.bias) if ln else x_loc
+    w_qkv = torch.cat([layer.q_linear.weight, layer.k_linear.weight, layer.v_linear.weight], 0)
+    b_qkv = torch.cat([layer.q_linear.bias, layer.k_linear.bias, layer.v_linear.bias], 0)
+    return ops.linear(xn, w_qkv, b_qkv)
+
+
+def _finish(layer, ctxv, x_loc):
+    o = ops.linear(ctxv, layer.output_proj.weight, layer.output_proj.bias)
+    if layer.use_layer_norm:
+        return ops.layer_norm(o, layer.layer_norm2.weight, layer.layer_norm2.bias, res=x_loc)
+    return ops.add(o, x_loc)
 
 
 def geometric_layer_part(layer, x_loc: torch.Tensor, csr: CSR, comm, n_src: int) -> torch.Tensor:
     """``GeometricAttention.forward`` (reference geometric_attention.py:518-598) on this rank's node slice.
     ``layer`` is a ``tagan_b200.GeometricAttention`` with replicated weights."""
-    ln = layer.use_layer_norm
-    xn = ops.layer_norm(x_loc, layer.layer_norm1.weight, layer.layer_norm1.bias) if ln else x_loc
-    w_qkv = torch.cat([layer.q_linear.weight, layer.k_linear.weight, layer.v_linear.weight], 0)
-    b_qkv = torch.cat([layer.q_linear.bias, layer.k_linear.bias, layer.v_linear.bias], 0)
-    qkv = ops.linear(xn, w_qkv, b_qkv)
+    qkv = _project(layer, x_loc)
     ctxv = geo_attention_core_part(qkv, csr, comm, layer.num_heads, layer.distance_metric, n_src,
                                    getattr(layer, "distance_param", None))
-    o = ops.linear(ctxv, layer.output_proj.weight, layer.output_proj.bias)
-    if ln:
-        return ops.layer_norm(o, layer.layer_norm2.weight, layer.layer_norm2.bias, res=x_loc)
-    return ops.add(o, x_loc)
+    return _finish(layer, ctxv, x_loc)
+
+
+def geometric_stage_part(layer, xs_loc, csrs, comm, n_src: int):
+    """The geometric layer over all T snapshots of a node-partitioned graph, software-pipelined: the projection
+    and the halo all-gather of snapshot t+1 are issued before the attention kernel of snapshot t, so the NVLink
+    transfer runs under the kernels (and, by the construction of the autograd graph, the reduce-scatter of
+    snapshot t runs under the backward kernels of snapshot t-1)."""
+    t_steps = len(xs_loc)
+    mid = ops.METRIC_ID[layer.distance_metric]
+    param = getattr(layer, "distance_param", None)
+    halos = [_Halo() for _ in range(t_steps)]
+    qkv = [None] * t_steps
+    kv = [None] * t_steps
+    outs = []
+    qkv[0] = _project(layer, xs_loc[0])
+    kv[0] = _HaloGatherFn.apply(qkv[0], comm, halos[0])
+    for t in range(t_steps):
+        if t + 1 < t_steps:
+            qkv[t + 1] = _project(layer, xs_loc[t + 1])
+            kv[t + 1] = _HaloGatherFn.apply(qkv[t + 1], comm, halos[t + 1])
+        ctxv = _PartGeoAttnFn.apply(qkv[t], kv[t], param, csrs[t], comm, halos[t], layer.num_heads, mid, n_src)
+        outs.append(_finish(layer, ctxv, xs_loc[t]))
+        qkv[t] = kv[t] = None
+    return outs

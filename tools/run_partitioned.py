@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--stage-snapshots", type=int, default=8, help="snapshots of the pipelined geometric-stage timing")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -105,13 +106,49 @@ def main():
                 acc[k].append(ev[k][0].elapsed_time(ev[k][1]))
     med = torch.tensor([sorted(acc[k])[len(acc[k]) // 2] for k in names], device=dev)
     dist.all_reduce(med, op=dist.ReduceOp.MAX)
+    # ---------------- pipelined geometric stage over several snapshots (fwd + bwd, weights replicated) ----------------
+    ts_n = a.stage_snapshots
+    layer = tagan_b200.GeometricAttention(hdim, heads, dropout=0.0, distance_metric="euclidean").to(dev)
+    gen = torch.Generator().manual_seed(100 + rank)
+    xs = [torch.randn(hi - lo, hdim, generator=gen).to(dev).requires_grad_(True) for _ in range(ts_n)]
+    eis = [synth.random_edges(n, e, torch.Generator().manual_seed(50 + s_), w.graph).to(dev) for s_ in range(ts_n)]
+    stage = {}
+    for mode in ("sequential", "pipelined"):
+        times = []
+        for it in range(3):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            csrs = [partitioned.build_csr_part(ei_, part, rank) for ei_ in eis]
+            if mode == "pipelined":
+                outs = partitioned.geometric_stage_part(layer, xs, csrs, comm, n)
+            else:
+                outs = [partitioned.geometric_layer_part(layer, x_, c_, comm, n) for x_, c_ in zip(xs, csrs)]
+            loss = sum(o.square().mean() for o in outs)
+            loss.backward()
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 1:
+                times.append(e0.elapsed_time(e1))
+            layer.zero_grad()
+            for x_ in xs:
+                x_.grad = None
+            del outs, loss, csrs
+        tt = torch.tensor([min(times)], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        stage[mode] = float(tt)
     if rank == 0:
         t = dict(zip(names, [float(v) for v in med]))
         # "fwd" includes one all-gather, "bwd_kernels" one reduce-scatter
         total = t["csr"] + t["fwd"] + t["bwd_kernels"]
         print(json.dumps({"world": world, "workload": w.name, "parity": parity, "ms": t,
                           "kernel_a_step_ms": total, "edge_snapshots_per_s": e / (total * 1e-3),
-                          "halo_bytes_per_rank": (n - (hi - lo)) * 2 * hdim * 4}), flush=True)
+                          "halo_bytes_per_rank": (n - (hi - lo)) * 2 * hdim * 4,
+                          "geometric_stage": {"snapshots": ts_n, "ms": stage,
+                                              "edge_snapshots_per_s_pipelined": e * ts_n / (stage["pipelined"] * 1e-3),
+                                              "edge_snapshots_per_s_sequential": e * ts_n / (stage["sequential"] * 1e-3)}}),
+              flush=True)
     dist.destroy_process_group()
 
 
