@@ -55,24 +55,36 @@ def build_csr_part(edge_index: torch.Tensor, part: NodePartition, rank: int, tra
 class TorchDistComm:
     """all_gather / reduce_scatter of equal-size blocks over a torch.distributed group (NCCL).
 
-    Both collectives are started asynchronously (NCCL's own stream) and return a ``wait`` callable; the caller
-    decides when the compute stream has to wait, which is what lets the exchange of snapshot t+1 overlap the
-    kernels of snapshot t (forward) and the reduce-scatter of snapshot t overlap the backward of snapshot t-1."""
+    The ``*_async`` forms enqueue the collective on a side stream of this object and return ``(out, wait)``:
+    ``wait()`` makes the *caller's current* stream wait for the collective.  The caller decides when that has
+    to happen, which is what lets the exchange of snapshot t+1 overlap the kernels of snapshot t (forward) and
+    the reduce-scatter of snapshot t overlap the backward of snapshot t-1.  The input is kept alive by the
+    ``wait`` closure, so drop the closure after calling it."""
 
     def __init__(self, part: NodePartition, rank: int, group=None):
         self.part, self.rank, self.group = part, rank, group
         assert part.num_nodes % part.world == 0, "equal blocks required (pad the graph to a multiple of world)"
+        self.stream = torch.cuda.Stream()
+
+    def _side(self, fn, out, inp):
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)                       # inp (and the allocation of out) are ready
+        with torch.cuda.stream(self.stream):
+            fn(out, inp, group=self.group)                 # blocking form: the side stream waits for NCCL's stream
+            done = self.stream.record_event()
+
+        def wait(_keep=(inp, out)):
+            torch.cuda.current_stream().wait_event(done)
+        return out, wait
 
     def all_gather_rows_async(self, local: torch.Tensor):
         out = torch.empty(self.part.num_nodes, local.shape[1], dtype=local.dtype, device=local.device)
-        work = dist.all_gather_into_tensor(out, local.contiguous(), group=self.group, async_op=True)
-        return out, work.wait
+        return self._side(dist.all_gather_into_tensor, out, local.contiguous())
 
     def reduce_scatter_rows_async(self, full: torch.Tensor):
         n_loc = self.part.num_nodes // self.part.world
         out = torch.empty(n_loc, full.shape[1], dtype=full.dtype, device=full.device)
-        work = dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group, async_op=True)
-        return out, work.wait
+        return self._side(dist.reduce_scatter_tensor, out, full.contiguous())
 
     def all_gather_rows(self, local):
         out, wait = self.all_gather_rows_async(local)
@@ -118,7 +130,7 @@ class _HaloGatherFn(torch.autograd.Function):
         halo.rs_wait()
         halo.dqkv[:, h:] = halo.rs_out
         out = halo.dqkv
-        halo.dqkv = halo.rs_out = None
+        halo.dqkv = halo.rs_out = halo.rs_wait = None
         return out, None, None
 
 
@@ -130,6 +142,7 @@ class _PartGeoAttnFn(torch.autograd.Function):
         n_loc, three_h = qkv2.shape
         h = three_h // 3
         halo.gather_wait()                                           # compute stream waits for the halo only now
+        halo.gather_wait = None
         ctxv = torch.empty(n_loc, h, dtype=torch.float32, device=qkv2.device)
         lse = torch.empty(n_loc, heads, dtype=torch.float32, device=qkv2.device)
         k_ptr, v_ptr = C.c_void_p(kv.data_ptr()), C.c_void_p(kv.data_ptr() + h * 4)

@@ -106,6 +106,10 @@ def main():
                 acc[k].append(ev[k][0].elapsed_time(ev[k][1]))
     med = torch.tensor([sorted(acc[k])[len(acc[k]) // 2] for k in names], device=dev)
     dist.all_reduce(med, op=dist.ReduceOp.MAX)
+    del ctx, kv, full, csr, qkv, dctx
+    mem = lambda tag: print(f"[mem r{rank}] {tag}: alloc {torch.cuda.memory_allocated() / 2**30:.1f} GiB, "
+                            f"peak {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", file=sys.stderr, flush=True)
+    mem("after micro timings")
     # ---------------- pipelined geometric stage over several snapshots (fwd + bwd, weights replicated) ----------------
     ts_n = a.stage_snapshots
     layer = tagan_b200.GeometricAttention(hdim, heads, dropout=0.0, distance_metric="euclidean").to(dev)
@@ -113,6 +117,7 @@ def main():
     xs = [torch.randn(hi - lo, hdim, generator=gen).to(dev).requires_grad_(True) for _ in range(ts_n)]
     eis = [synth.random_edges(n, e, torch.Generator().manual_seed(50 + s_), w.graph).to(dev) for s_ in range(ts_n)]
     stage = {}
+    keep = {}
     for mode in ("sequential", "pipelined"):
         times = []
         for it in range(3):
@@ -131,13 +136,21 @@ def main():
             torch.cuda.synchronize()
             if it >= 1:
                 times.append(e0.elapsed_time(e1))
+            if it == 2:                                       # pipelined == sequential: outputs and input gradients
+                keep[mode] = ([o.detach()[:4096].clone() for o in outs], [x_.grad[:4096].clone() for x_ in xs])
             layer.zero_grad()
             for x_ in xs:
                 x_.grad = None
             del outs, loss, csrs
+            mem(f"{mode} it{it}")
         tt = torch.tensor([min(times)], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         stage[mode] = float(tt)
+    same = all(torch.equal(p_, s_) for k_ in (0, 1) for p_, s_ in zip(keep["pipelined"][k_], keep["sequential"][k_]))
+    flag = torch.tensor([1.0 if same else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    parity["pipelined_equals_sequential"] = bool(flag.item() == 1.0)
+    assert parity["pipelined_equals_sequential"]
     if rank == 0:
         t = dict(zip(names, [float(v) for v in med]))
         # "fwd" includes one all-gather, "bwd_kernels" one reduce-scatter
