@@ -435,8 +435,10 @@ TAGAN_API int tagan_tattn_bwd(const float* Q, const float* K, const float* V, in
     default: rc = set_smem(tattn_bwd_kernel<64>, c.smem); break;
   }
   if (rc) return rc;
-  const bool fast = T <= 32 && c.warps * c.PPW >= heads && !per_node && c.smem <= 48 * 1024;
-  if (fast && tagan_tattn_bwd_fast_launch(D, c.TP, grid, c.warps * 32, c.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
+  Cfg cf;                                                // the fast kernel parks P and dS in smem: larger slots
+  const bool fast = T <= 32 && !per_node && make_cfg(T, D, heads, tattn_bwd_fast_slot_floats(T, D, c.TP), &cf) &&
+                    cf.warps * cf.PPW >= heads && cf.smem <= 72 * 1024;
+  if (fast && tagan_tattn_bwd_fast_launch(D, cf.TP, grid, cf.warps * 32, cf.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
                                           ctx, lse, dctx, dQ, dK, dV, ldd, db_target)) {
   } else {
     DISPATCH_D(tattn_bwd_kernel, <<<grid, c.warps * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, bias_t, bias_bstride, ms, ctx, lse, dctx, dQ, dK, dV, ldd, db_target, per_node ? 1 : 0, c.TP, c.warps))

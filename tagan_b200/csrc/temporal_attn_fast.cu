@@ -107,8 +107,12 @@ tattn_fwd_fast_kernel(const float* __restrict__ Q, const float* __restrict__ K, 
   }
 }
 
+// Backward: phase 1 (lane = query row i) recomputes the probabilities from the saved log-sum-exp, forms
+// dS = P o (dP - delta), accumulates dQ in registers and parks P and dS*scale in shared memory (pitch TP+1, so a
+// lane's row-wise stores and the column-wise loads of phase 2 are both conflict-free); phase 2 (lane = key row j)
+// reads its column of P / dS back and accumulates dV = P^T dO and dK = dS^T Q -- no second exp or dot product.
 template <int D, int TP>
-__global__ void __launch_bounds__(MAX_WARPS * 32)
+__global__ void __launch_bounds__(MAX_WARPS * 32, (D <= 16 && D * TP <= 256) ? 2 : 1)
 tattn_bwd_fast_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                       int64_t B, int T, int heads, int64_t rsb, int64_t rst, const float* __restrict__ bias, MaskSpec ms,
                       const float* __restrict__ ctx, const float* __restrict__ lse, const float* __restrict__ dctx,
@@ -116,29 +120,30 @@ tattn_bwd_fast_kernel(const float* __restrict__ Q, const float* __restrict__ K, 
                       float* __restrict__ dbias_partial /* [grid, h, T, T] or null */) {
   extern __shared__ __align__(16) float smem[];
   constexpr int PPW = 32 / TP;
+  constexpr int PT = TP + 1;
   const int H = heads * D;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / TP, li = lane - sub * TP;
   const int tpad = (T + 3) & ~3;
-  const int slot_floats = 4 * T * D + 3 * tpad;
+  const int slot_floats = tattn_bwd_fast_slot_floats(T, D, TP);
   float* slot = smem + (size_t)(w * PPW + sub) * slot_floats;
   float* Qs = slot;
   float* Ks = Qs + T * D;
   float* Vs = Ks + T * D;
   float* Gs = Vs + T * D;
-  float* lse_s = Gs + T * D;
-  float* del_s = lse_s + tpad;
-  float* ts_s = del_s + tpad;
+  float* Ps = Gs + T * D;            // [T][PT] probabilities
+  float* Ss = Ps + TP * PT;          // [T][PT] dS * scale
+  float* ts_s = Ss + TP * PT;
+  (void)tpad;
   const float scale = 1.f / sqrtf((float)D);
   const bool causal = (ms.flags & 1) || ((ms.flags & 4) && ms.allones_flag && *ms.allones_flag != 0);
   const int hd = w * PPW + sub;
   const bool pv = hd < heads;
   const bool rv = pv && li < T;
-  float brow[TP], bcol[TP], dbrow[TP];
+  float brow[TP], dbrow[TP];
 #pragma unroll
   for (int j = 0; j < TP; ++j) {
     brow[j] = (bias && rv && j < T) ? bias[((int64_t)hd * T + li) * T + j] : 0.f;   // lane = query i, over keys j
-    bcol[j] = (bias && rv && j < T) ? bias[((int64_t)hd * T + j) * T + li] : 0.f;   // lane = key j, over queries i
     dbrow[j] = 0.f;
   }
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
@@ -151,18 +156,19 @@ tattn_bwd_fast_kernel(const float* __restrict__ Q, const float* __restrict__ K, 
       load_tile<D>(Gs, dctx + b * rsb * (int64_t)H + (int64_t)hd * D, rst * H, T, li, TP);
       if (ms.ts) for (int t = li; t < T; t += TP) ts_s[t] = ms.ts[b * T + t];
     }
-    __syncwarp();
+    float dl = 0.f, ls2 = 0.f;
     if (rv) {
       const float* cp = ctx + (b * rsb + li * rst) * (int64_t)H + (int64_t)hd * D;
-      float dl = 0.f;
+      const float* gp = dctx + (b * rsb + li * rst) * (int64_t)H + (int64_t)hd * D;
+      float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int c = 0; c < D; c += 4) {
-        float4 c4 = __ldg(reinterpret_cast<const float4*>(cp + c));
-        const float* g = Gs + li * D + c;
-        dl = fmaf(g[0], c4.x, dl); dl = fmaf(g[1], c4.y, dl); dl = fmaf(g[2], c4.z, dl); dl = fmaf(g[3], c4.w, dl);
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cp + c));
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gp + c));
+        d0 = fmaf(g4.x, c4.x, d0); d1 = fmaf(g4.y, c4.y, d1); d0 = fmaf(g4.z, c4.z, d0); d1 = fmaf(g4.w, c4.w, d1);
       }
-      del_s[li] = dl;
-      lse_s[li] = lse[(b * heads + hd) * T + li];
+      dl = d0 + d1;
+      ls2 = lse[(b * heads + hd) * T + li] * LOG2E;
     }
     __syncwarp();
     const uint8_t* mbase = nullptr;
@@ -172,21 +178,37 @@ tattn_bwd_fast_kernel(const float* __restrict__ Q, const float* __restrict__ K, 
       const int i = li;
       float q[D], g[D], dq[D];
 #pragma unroll
-      for (int c = 0; c < D; ++c) { q[c] = rv ? Qs[i * D + c] : 0.f; g[c] = rv ? Gs[i * D + c] : 0.f; dq[c] = 0.f; }
-      const float ls2 = rv ? lse_s[i] * LOG2E : 0.f, dl = rv ? del_s[i] : 0.f;
+      for (int c = 0; c < D; c += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(Qs + (rv ? i : 0) * D + c);
+        const float4 g4 = *reinterpret_cast<const float4*>(Gs + (rv ? i : 0) * D + c);
+        q[c] = q4.x; q[c + 1] = q4.y; q[c + 2] = q4.z; q[c + 3] = q4.w;
+        g[c] = g4.x; g[c + 1] = g4.y; g[c + 2] = g4.z; g[c + 3] = g4.w;
+        dq[c] = dq[c + 1] = dq[c + 2] = dq[c + 3] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < TP; ++j) {
         if (j < T) {
-          const float sv = dot_smem<D>(q, Ks + j * D) * scale + brow[j];
+          const float* kr = Ks + j * D;
+          const float* vr = Vs + j * D;
+          float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+          float kreg[D];
+#pragma unroll
+          for (int c = 0; c < D; c += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(kr + c);
+            const float4 v4 = *reinterpret_cast<const float4*>(vr + c);
+            kreg[c] = k4.x; kreg[c + 1] = k4.y; kreg[c + 2] = k4.z; kreg[c + 3] = k4.w;
+            s0 = fmaf(q[c], k4.x, s0); s1 = fmaf(q[c + 1], k4.y, s1); s0 = fmaf(q[c + 2], k4.z, s0); s1 = fmaf(q[c + 3], k4.w, s1);
+            p0 = fmaf(g[c], v4.x, p0); p1 = fmaf(g[c + 1], v4.y, p1); p0 = fmaf(g[c + 2], v4.z, p0); p1 = fmaf(g[c + 3], v4.w, p1);
+          }
+          const float sv = (s0 + s1) * scale + brow[j];
           const bool kv = rv && key_valid(ms, causal, ms.ts ? ts_s : nullptr, mbase, T, i, j) && sv > -INFINITY;
           const float pr = kv ? exp2f(sv * LOG2E - ls2) : 0.f;
-          const float dp = dot_smem<D>(g, Vs + j * D);
-          const float ds = pr * (dp - dl);
+          const float ds = pr * ((p0 + p1) - dl);
           dbrow[j] += ds;
           const float dss = ds * scale;
-          const float* kr = Ks + j * D;
+          if (rv) { Ps[i * PT + j] = pr; Ss[i * PT + j] = dss; }
 #pragma unroll
-          for (int c = 0; c < D; ++c) dq[c] = fmaf(dss, kr[c], dq[c]);
+          for (int c = 0; c < D; ++c) dq[c] = fmaf(dss, kreg[c], dq[c]);
         }
       }
       if (rv) {
@@ -195,23 +217,28 @@ tattn_bwd_fast_kernel(const float* __restrict__ Q, const float* __restrict__ K, 
         for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(op + c) = make_float4(dq[c], dq[c + 1], dq[c + 2], dq[c + 3]);
       }
     }
+    __syncwarp();
     {   // ---- phase 2: lane = key row j
       const int j = li;
-      float k[D], v[D], dk[D], dv[D];
+      float dk[D], dv[D];
 #pragma unroll
-      for (int c = 0; c < D; ++c) { k[c] = rv ? Ks[j * D + c] : 0.f; v[c] = rv ? Vs[j * D + c] : 0.f; dk[c] = 0.f; dv[c] = 0.f; }
+      for (int c = 0; c < D; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
 #pragma unroll
       for (int i = 0; i < TP; ++i) {
         if (i < T) {
-          const float sv = dot_smem<D>(k, Qs + i * D) * scale + bcol[i];
-          const bool kv = rv && key_valid(ms, causal, ms.ts ? ts_s : nullptr, mbase, T, i, j) && sv > -INFINITY;
-          const float pr = kv ? exp2f((sv - lse_s[i]) * LOG2E) : 0.f;
+          const float pr = rv ? Ps[i * PT + j] : 0.f;
+          const float dss = rv ? Ss[i * PT + j] : 0.f;
           const float* gr = Gs + i * D;
-          const float dp = dot_smem<D>(v, gr);
-          const float dss = pr * (dp - del_s[i]) * scale;
           const float* qr = Qs + i * D;
 #pragma unroll
-          for (int c = 0; c < D; ++c) { dv[c] = fmaf(pr, gr[c], dv[c]); dk[c] = fmaf(dss, qr[c], dk[c]); }
+          for (int c = 0; c < D; c += 4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gr + c);
+            const float4 q4 = *reinterpret_cast<const float4*>(qr + c);
+            dv[c] = fmaf(pr, g4.x, dv[c]); dv[c + 1] = fmaf(pr, g4.y, dv[c + 1]);
+            dv[c + 2] = fmaf(pr, g4.z, dv[c + 2]); dv[c + 3] = fmaf(pr, g4.w, dv[c + 3]);
+            dk[c] = fmaf(dss, q4.x, dk[c]); dk[c + 1] = fmaf(dss, q4.y, dk[c + 1]);
+            dk[c + 2] = fmaf(dss, q4.z, dk[c + 2]); dk[c + 3] = fmaf(dss, q4.w, dk[c + 3]);
+          }
         }
       }
       if (rv) {
@@ -236,6 +263,20 @@ tattn_bwd_fast_kernel(const float* __restrict__ Q, const float* __restrict__ K, 
 
 // instantiated (D, TP) pairs: head dims 8/16/32 x padded lengths 8/16/32 (except 32x32, whose unrolled body is
 // too large to pay off); everything else takes the generic kernels
+template <int D, int TP>
+void tattn_bwd_fast_launch_one(int grid, int threads, size_t smem, cudaStream_t st, const float* Q, const float* K,
+                               const float* V, int64_t ld, int64_t B, int T, int heads, int64_t rsb, int64_t rst,
+                               const float* bias, MaskSpec ms, const float* ctx, const float* lse, const float* dctx,
+                               float* dQ, float* dK, float* dV, int64_t ldd, float* dbias_partial) {
+  static size_t opted = 0;                      // per instantiation; raising the limit is idempotent
+  if (smem > 48 * 1024 && smem > opted) {
+    cudaFuncSetAttribute(tattn_bwd_fast_kernel<D, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    opted = smem;
+  }
+  tattn_bwd_fast_kernel<D, TP><<<grid, threads, smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, ms, ctx, lse, dctx,
+                                                           dQ, dK, dV, ldd, dbias_partial);
+}
+
 #define FAST_CASES(FN, ...)                                    \
   switch (D * 64 + TP) {                                       \
     case 8 * 64 + 8: FN<8, 8> __VA_ARGS__; return true;               \
@@ -261,5 +302,6 @@ bool tagan_tattn_bwd_fast_launch(int D, int TP, int grid, int threads, size_t sm
                                  const float* K, const float* V, int64_t ld, int64_t B, int T, int heads, int64_t rsb,
                                  int64_t rst, const float* bias, MaskSpec ms, const float* ctx, const float* lse,
                                  const float* dctx, float* dQ, float* dK, float* dV, int64_t ldd, float* dbias_partial) {
-  FAST_CASES(tattn_bwd_fast_kernel, <<<grid, threads, smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, ms, ctx, lse, dctx, dQ, dK, dV, ldd, dbias_partial))
+  FAST_CASES(tattn_bwd_fast_launch_one, (grid, threads, smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms, ctx, lse, dctx, dQ, dK, dV, ldd, dbias_partial))
 }
+

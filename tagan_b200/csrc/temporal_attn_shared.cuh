@@ -25,6 +25,11 @@ __device__ __forceinline__ bool key_valid(const MaskSpec& ms, bool causal, const
   return v;
 }
 
+// floats of shared memory per (head) slot of the fast backward kernel: Q,K,V,dO tiles, P and dS (pitch TP+1), ts
+__host__ __device__ inline int tattn_bwd_fast_slot_floats(int T, int D, int TP) {
+  return 4 * T * D + 2 * TP * (TP + 1) + ((T + 3) & ~3) + (((2 * TP * (TP + 1)) & 3) ? 4 - ((2 * TP * (TP + 1)) & 3) : 0);
+}
+
 template <int D>
 __device__ __forceinline__ float dot_smem(const float* q, const float* ks) {
   float s = 0.f;
