@@ -5,14 +5,19 @@
 //
 // Warp roles of the persistent CTA (one per SM, 14 warps):
 //   warps 0-3   epilogue  : tcgen05.ld -> padded smem -> row-contiguous 128 B stores (+bias / +C)
-//   warp  4     MMA       : one thread issues tcgen05.mma.kind::tf32 (lo.lo, lo.hi, hi.lo, hi.hi per k-step)
+//   warp  4     MMA       : one thread issues tcgen05.mma.kind::tf32 (lo.hi, hi.lo, hi.hi per k-step); the A operand
+//                           is read from TENSOR MEMORY (lane = row), B through a shared-memory descriptor
 //   warp  5     TMA       : one thread issues cp.async.bulk.tensor loads of the raw fp32 A/B tiles straight
 //                           into their final 128B-swizzled positions (K-major: one 128x32 box with
 //                           SWIZZLE_128B; MN-major: four 32x32 boxes with SWIZZLE_128B_ATOM_32B), completing
 //                           on an mbarrier with expect_tx; it runs up to STAGES k-blocks ahead, so the HBM
 //                           stream is never exposed to thread-level latency and costs no registers
-//   warps 6-13  split     : smem -> smem, layout-agnostic: hi = rn_tf32(x) in place, lo = rn_tf32(x - hi) into
-//                           the twin tile, fence.proxy.async, arrive on the stage's "full" barrier
+//   warps 6-13  split     : A: raw smem tile -> registers -> hi = rn_tf32(x), lo = rn_tf32(x - hi) -> tcgen05.st into the
+//                           stage's TMEM columns (a thread owns one row; the two warps of a TMEM lane quarter take
+//                           half of the k-columns each), which removes A_hi/A_lo from shared memory altogether
+//                           (a 128x128 tf32 MMA fed from smem alone needs ~120 B/clk of the 128 B/clk smem port);
+//                           B (only when it is not a pre-split weight): smem -> smem in place + twin tile,
+//                           fence.proxy.async; then arrive on the stage's "full" barrier
 // Out-of-range rows / columns / K tail are zero-filled by TMA itself, so there is no edge-tile code path.
 #include "common.cuh"
 #include <cuda.h>
@@ -20,15 +25,18 @@
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;             // raw A, B_hi, B_lo
 constexpr int EPI_WARPS = 4, SPLIT_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS, TMA_WARP = EPI_WARPS + 1, SPLIT_WARP0 = EPI_WARPS + 2;
 constexpr int THREADS = (EPI_WARPS + 2 + SPLIT_WARPS) * 32;   // 448
 constexpr int SPLIT_THREADS = SPLIT_WARPS * 32;
-constexpr int TMEM_COLS = ACC_STAGES * BN;
+constexpr int A_TMEM_COL0 = ACC_STAGES * BN;            // A operand stages live behind the accumulators:
+constexpr int A_TMEM_STAGE_COLS = 2 * BK;               //   per stage 32 columns of A_hi, 32 of A_lo (lane = row)
+constexpr int TMEM_COLS = 512;                          // 256 (accumulators) + STAGES * 64, rounded to a power of two
+static_assert(A_TMEM_COL0 + STAGES * A_TMEM_STAGE_COLS <= TMEM_COLS, "TMEM budget");
 constexpr int EPI_PITCH = 36;
 constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH * 4;
 constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + (size_t)EPI_WARPS * EPI_STAGE_BYTES;
@@ -56,9 +64,29 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n }"
-               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// A operand read from tensor memory (lane = row of the 128-row tile, one tf32 per 32-bit column)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n }"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
@@ -115,7 +143,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
-  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES + 256);
+  const uint32_t epi_u32 = smem_u32(smem + (size_t)STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -160,14 +188,14 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
             for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &tmA, m0 + 32 * b, (int)k0, &raw_bar[stage]);
           }
           if (!p.b_mn_major) {
-            tma_load_2d(st + 2 * TILE_BYTES, &tmB, (int)k0, n0, &raw_bar[stage]);
-            if (p.b_presplit) tma_load_2d(st + 3 * TILE_BYTES, &tmB2, (int)k0, n0, &raw_bar[stage]);
+            tma_load_2d(st + TILE_BYTES, &tmB, (int)k0, n0, &raw_bar[stage]);
+            if (p.b_presplit) tma_load_2d(st + 2 * TILE_BYTES, &tmB2, (int)k0, n0, &raw_bar[stage]);
           } else {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) tma_load_2d(st + 2 * TILE_BYTES + b * 4096, &tmB, n0 + 32 * b, (int)k0, &raw_bar[stage]);
+            for (int b = 0; b < 4; ++b) tma_load_2d(st + TILE_BYTES + b * 4096, &tmB, n0 + 32 * b, (int)k0, &raw_bar[stage]);
             if (p.b_presplit) {
 #pragma unroll
-              for (int b = 0; b < 4; ++b) tma_load_2d(st + 3 * TILE_BYTES + b * 4096, &tmB2, n0 + 32 * b, (int)k0, &raw_bar[stage]);
+              for (int b = 0; b < 4; ++b) tma_load_2d(st + 2 * TILE_BYTES + b * 4096, &tmB2, n0 + 32 * b, (int)k0, &raw_bar[stage]);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -185,18 +213,53 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
       for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
         mbar_wait(&raw_bar[stage], phase);                   // TMA bytes have landed
-        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-        const int nchunk = p.b_presplit ? 1024 / SPLIT_THREADS : 2048 / SPLIT_THREADS;
+        const uint32_t st_u32 = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        {
+          // ---- A: raw smem tile -> registers -> hi/lo -> tensor memory.  A warp owns TMEM lanes 32*(warp%4)..+31, so
+          // the two split warps of a lane quarter take 16 of the 32 k-columns each; a thread handles its own row.
+          const int quarter = warp & 3, half = (warp - SPLIT_WARP0) >> 2;
+          const int row = quarter * 32 + lane;
+          uint32_t hi[16], lo[16];
+          if (!p.a_mn_major) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = half * 4 + i;                                   // 16-byte chunk of the 128-byte row
+              const float4 v = lds128(st_u32 + row * 128 + ((c ^ (row & 7)) << 4));
+              const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float h = tf32_rn(x[q]);
+                hi[i * 4 + q] = __float_as_uint(h);
+                lo[i * 4 + q] = __float_as_uint(tf32_rn(x[q] - h));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {                               // boxes [32 k][32 m], unswizzled
+              const float x = lds32(st_u32 + (row >> 5) * 4096 + (half * 16 + kk) * 128 + (row & 31) * 4);
+              const float h = tf32_rn(x);
+              hi[kk] = __float_as_uint(h);
+              lo[kk] = __float_as_uint(tf32_rn(x - h));
+            }
+          }
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                 (uint32_t)(A_TMEM_COL0 + stage * A_TMEM_STAGE_COLS + half * 16);
+          tmem_st16(taddr, hi);
+          tmem_st16(taddr + BK, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          if (!p.b_presplit) {
 #pragma unroll 4
-        for (int i = 0; i < nchunk; ++i) {
-          const int chunk = tt + SPLIT_THREADS * i;          // [0,1024): A tile, [1024,2048): B tile
-          uint8_t* hi = st + (chunk >> 10) * (2 * TILE_BYTES) + (chunk & 1023) * 16;
-          const float4 v = *reinterpret_cast<const float4*>(hi);
-          float4 h, l;
-          h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
-          l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
-          *reinterpret_cast<float4*>(hi) = h;
-          *reinterpret_cast<float4*>(hi + TILE_BYTES) = l;
+            for (int i = 0; i < 1024 / SPLIT_THREADS; ++i) {
+              const uint32_t bh = st_u32 + TILE_BYTES + (tt + SPLIT_THREADS * i) * 16;
+              const float4 v = lds128(bh);
+              float4 h, l;
+              h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+              l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+              sts128(bh, h);
+              sts128(bh + TILE_BYTES, l);
+            }
+          }
+          tc_fence_before();
         }
         fence_proxy_async();
         __syncwarp();
@@ -211,10 +274,10 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       uint32_t phase = 0, acc_phase = 0;
       // per k-step (8 tf32 = 32 bytes) descriptor advance: +32 B inside the swizzle row (K-major),
       // +1024 B = two 4-row k-atoms further (MN-major)
-      const uint32_t a_step = p.a_mn_major ? 1024u : 32u, b_step = p.b_mn_major ? 1024u : 32u;
-      const uint32_t a_lbo = p.a_mn_major ? 4096u : 16u, b_lbo = p.b_mn_major ? 4096u : 16u;
-      const uint32_t a_sbo = p.a_mn_major ? 512u : 1024u, b_sbo = p.b_mn_major ? 512u : 1024u;
-      const uint32_t a_lay = p.a_mn_major ? 1u : 2u, b_lay = p.b_mn_major ? 1u : 2u;
+      const uint32_t b_step = p.b_mn_major ? 1024u : 32u;
+      const uint32_t b_lbo = p.b_mn_major ? 4096u : 16u;
+      const uint32_t b_sbo = p.b_mn_major ? 512u : 1024u;
+      const uint32_t b_lay = p.b_mn_major ? 1u : 2u;
       for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
         const int64_t kbeg = (int64_t)ks * p.k_per_split;
@@ -229,21 +292,21 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t da_hi = make_desc(sbase + kk * a_step, a_lbo, a_sbo, a_lay);
-            const uint64_t da_lo = make_desc(sbase + TILE_BYTES + kk * a_step, a_lbo, a_sbo, a_lay);
-            const uint64_t db_hi = make_desc(sbase + 2 * TILE_BYTES + kk * b_step, b_lbo, b_sbo, b_lay);
-            const uint64_t db_lo = make_desc(sbase + 3 * TILE_BYTES + kk * b_step, b_lbo, b_sbo, b_lay);
+            const uint64_t db_hi = make_desc(sbase + TILE_BYTES + kk * b_step, b_lbo, b_sbo, b_lay);
+            const uint64_t db_lo = make_desc(sbase + 2 * TILE_BYTES + kk * b_step, b_lbo, b_sbo, b_lay);
+            const uint32_t ta_hi = tmem_base + (uint32_t)(A_TMEM_COL0 + stage * A_TMEM_STAGE_COLS + kk * 8);
+            const uint32_t ta_lo = ta_hi + BK;
             if (p.passes == 4) {
-              umma_tf32(tmem_d, da_lo, db_lo, p.idesc, accum);   // small terms first
-              umma_tf32(tmem_d, da_lo, db_hi, p.idesc, 1);
-              umma_tf32(tmem_d, da_hi, db_lo, p.idesc, 1);
-              umma_tf32(tmem_d, da_hi, db_hi, p.idesc, 1);
+              umma_tf32_ts(tmem_d, ta_lo, db_lo, p.idesc, accum);   // small terms first
+              umma_tf32_ts(tmem_d, ta_lo, db_hi, p.idesc, 1);
+              umma_tf32_ts(tmem_d, ta_hi, db_lo, p.idesc, 1);
+              umma_tf32_ts(tmem_d, ta_hi, db_hi, p.idesc, 1);
             } else if (p.passes == 3) {
-              umma_tf32(tmem_d, da_lo, db_hi, p.idesc, accum);
-              umma_tf32(tmem_d, da_hi, db_lo, p.idesc, 1);
-              umma_tf32(tmem_d, da_hi, db_hi, p.idesc, 1);
+              umma_tf32_ts(tmem_d, ta_lo, db_hi, p.idesc, accum);
+              umma_tf32_ts(tmem_d, ta_hi, db_lo, p.idesc, 1);
+              umma_tf32_ts(tmem_d, ta_hi, db_hi, p.idesc, 1);
             } else {
-              umma_tf32(tmem_d, da_hi, db_hi, p.idesc, accum);
+              umma_tf32_ts(tmem_d, ta_hi, db_hi, p.idesc, accum);
             }
             accum = 1;
           }
@@ -269,6 +332,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       tc_fence_after();
       float* out = p.partial ? p.partial + (int64_t)ks * p.M * p.N : p.C;
       const int64_t ldo = p.partial ? p.N : p.ldc;
+      const bool interior = p.c_vec && ((int64_t)(mt + 1) * BM <= p.M) && (n0 + BN <= p.N) && !(p.partial == nullptr && p.accumulate);
+      const bool bias_vec = p.partial == nullptr && p.bias != nullptr;       // host guarantees 16-byte alignment when c_vec
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t r[32];
@@ -290,41 +355,57 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
         // registers (lane = row, 32 consecutive columns) -> padded smem tile -> row-contiguous 128-byte stores
-        float* stg = epi_stage + warp * (32 * EPI_PITCH);
+        const uint32_t stg = epi_u32 + (uint32_t)(warp * (32 * EPI_PITCH) * 4);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + j) =
-              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          sts128(stg + (uint32_t)((lane * EPI_PITCH + j) * 4),
+                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
         __syncwarp();
         const int64_t c0 = n0 + cc * 32 + (lane & 7) * 4;
-        const bool direct = p.partial == nullptr;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (direct && p.bias) {
-          if (c0 < p.N) b4.x = p.bias[c0];
-          if (c0 + 1 < p.N) b4.y = p.bias[c0 + 1];
-          if (c0 + 2 < p.N) b4.z = p.bias[c0 + 2];
-          if (c0 + 3 < p.N) b4.w = p.bias[c0 + 3];
-        }
+        const uint32_t src0 = stg + (uint32_t)(((lane >> 3) * EPI_PITCH + (lane & 7) * 4) * 4);
+        if (interior) {
+          // whole tile inside the matrix, 16-byte aligned rows, plain store: straight-line code
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias_vec) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+          float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + (lane >> 3);
-          const int64_t grow = (int64_t)mt * BM + warp * 32 + rr;
-          if (grow >= p.M || c0 >= p.N) continue;
-          float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + (lane & 7) * 4);
-          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-          float* orow = out + grow * ldo + c0;
-          if (c0 + 3 < p.N && p.c_vec) {
-            if (direct && p.accumulate) {
-              float4 o4 = *reinterpret_cast<const float4*>(orow);
-              v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
+          for (int i = 0; i < 8; ++i) v[i] = lds128(src0 + (uint32_t)(i * 4 * EPI_PITCH * 4));
+          float* orow = out + ((int64_t)mt * BM + warp * 32 + (lane >> 3)) * ldo + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
+            *reinterpret_cast<float4*>(orow + (int64_t)(i * 4) * ldo) = v[i];
+          }
+        } else {
+          const bool direct = p.partial == nullptr;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (direct && p.bias) {
+            if (c0 < p.N) b4.x = p.bias[c0];
+            if (c0 + 1 < p.N) b4.y = p.bias[c0 + 1];
+            if (c0 + 2 < p.N) b4.z = p.bias[c0 + 2];
+            if (c0 + 3 < p.N) b4.w = p.bias[c0 + 3];
+          }
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3);
+            const int64_t grow = (int64_t)mt * BM + warp * 32 + rr;
+            if (grow >= p.M || c0 >= p.N) continue;
+            float4 v = lds128(src0 + (uint32_t)(i * 4 * EPI_PITCH * 4));
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            float* orow = out + grow * ldo + c0;
+            if (c0 + 3 < p.N && p.c_vec) {
+              if (direct && p.accumulate) {
+                float4 o4 = *reinterpret_cast<const float4*>(orow);
+                v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
+              }
+              *reinterpret_cast<float4*>(orow) = v;
+            } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (c0 + q < p.N) orow[q] = (direct && p.accumulate) ? orow[q] + vv[q] : vv[q];
             }
-            *reinterpret_cast<float4*>(orow) = v;
-          } else {
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (c0 + q < p.N) orow[q] = (direct && p.accumulate) ? orow[q] + vv[q] : vv[q];
           }
         }
       }
@@ -413,7 +494,7 @@ EncodeFn get_encode() {
 
 // operand stored [rows, cols] row-major with leading dimension ld (floats).  K-major use: cols = K, box 32 x 128,
 // SWIZZLE_128B.  MN-major use: cols = M or N, rows = K, box 32 x 32, SWIZZLE_128B_ATOM_32B.
-bool make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld, bool mn_major) {
+bool make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld, bool mn_major, bool plain = false) {
   EncodeFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -422,7 +503,8 @@ bool make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, in
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   plain ? CU_TENSOR_MAP_SWIZZLE_NONE
+                         : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -472,12 +554,12 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
     p.partial = static_cast<float*>(workspace);
   }
   if (p.partial) p.c_vec = (N % 4 == 0);
-  else p.c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0);
-  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) | ((uint32_t)p.b_mn_major << 16) |
+  else p.c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | ((uint32_t)p.b_mn_major << 16) |
             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   CUtensorMap tmA, tmB, tmB2;
   // NT: A[M,K], B[N,K] (K-major).  NN: A[M,K], B[K,N] (MN-major).  TN: A[K,M], B[K,N] (both MN-major).
-  const bool okA = p.a_mn_major ? make_map(&tmA, A, K, M, lda, true) : make_map(&tmA, A, M, K, lda, false);
+  const bool okA = p.a_mn_major ? make_map(&tmA, A, K, M, lda, true, true) : make_map(&tmA, A, M, K, lda, false);
   p.b_presplit = 0;
   bool okB;
   if (want_presplit(op, N, K) && passes != 1) {
