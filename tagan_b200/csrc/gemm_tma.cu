@@ -78,6 +78,14 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// one lane of a converged warp; ptxas then knows the guarded region runs on a single thread and feeds the
+// uniform-register operands of UTCHMMA without a per-instruction waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n }" : "=r"(pred));
+  return pred != 0;
+}
+
 // A operand read from tensor memory (lane = row of the 128-row tile, one tf32 per 32-bit column)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n }"
@@ -162,7 +170,10 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // The CTA allocates all 512 columns, so the allocation can only start at lane 0 / column 0.  Treating the base
+  // as the constant 0 keeps every TMEM address of the MMA loop in uniform registers (no R2UR per instruction).
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
   const int64_t num_work = (int64_t)p.tiles_m * p.tiles_n * p.splits;
 
   if (warp == TMA_WARP) {
@@ -269,53 +280,58 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
     }
   } else if (warp == MMA_WARP) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      // per k-step (8 tf32 = 32 bytes) descriptor advance: +32 B inside the swizzle row (K-major),
-      // +1024 B = two 4-row k-atoms further (MN-major)
-      const uint32_t b_step = p.b_mn_major ? 1024u : 32u;
-      const uint32_t b_lbo = p.b_mn_major ? 4096u : 16u;
-      const uint32_t b_sbo = p.b_mn_major ? 512u : 1024u;
-      const uint32_t b_lay = p.b_mn_major ? 1u : 2u;
-      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
-        const int64_t kbeg = (int64_t)ks * p.k_per_split;
-        const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator stage
+    // The whole warp runs the (warp-uniform) control flow so that stage indices, descriptors and TMEM addresses
+    // live in uniform registers; only the tcgen05 instructions themselves are issued by lane 0.
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    // per k-step (8 tf32 = 32 bytes) descriptor advance: +32 B inside the swizzle row (K-major),
+    // +1024 B = two 4-row k-atoms further (MN-major)
+    const uint32_t b_step = p.b_mn_major ? 1024u : 32u;
+    const uint64_t b_desc0 = make_desc(0, p.b_mn_major ? 4096u : 16u, p.b_mn_major ? 512u : 1024u, p.b_mn_major ? 1u : 2u);
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t idesc = p.idesc;
+    const int passes = p.passes;
+    for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
+      const int64_t kbeg = (int64_t)ks * p.k_per_split;
+      const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
+      const int nkb = kend > kbeg ? (int)((kend - kbeg + BK - 1) / BK) : 0;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        uint32_t accum = 0;
-        for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        const uint32_t sbase = smem0 + (uint32_t)stage * STAGE_BYTES;
+        const uint32_t ta0 = tmem_base + (uint32_t)(A_TMEM_COL0 + stage * A_TMEM_STAGE_COLS);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t db_hi = make_desc(sbase + TILE_BYTES + kk * b_step, b_lbo, b_sbo, b_lay);
-            const uint64_t db_lo = make_desc(sbase + 2 * TILE_BYTES + kk * b_step, b_lbo, b_sbo, b_lay);
-            const uint32_t ta_hi = tmem_base + (uint32_t)(A_TMEM_COL0 + stage * A_TMEM_STAGE_COLS + kk * 8);
-            const uint32_t ta_lo = ta_hi + BK;
-            if (p.passes == 4) {
-              umma_tf32_ts(tmem_d, ta_lo, db_lo, p.idesc, accum);   // small terms first
-              umma_tf32_ts(tmem_d, ta_lo, db_hi, p.idesc, 1);
-              umma_tf32_ts(tmem_d, ta_hi, db_lo, p.idesc, 1);
-              umma_tf32_ts(tmem_d, ta_hi, db_hi, p.idesc, 1);
-            } else if (p.passes == 3) {
-              umma_tf32_ts(tmem_d, ta_lo, db_hi, p.idesc, accum);
-              umma_tf32_ts(tmem_d, ta_hi, db_lo, p.idesc, 1);
-              umma_tf32_ts(tmem_d, ta_hi, db_hi, p.idesc, 1);
+            const uint64_t db_hi = b_desc0 | (uint64_t)(((sbase + TILE_BYTES + kk * b_step) >> 4) & 0x3FFF);
+            const uint64_t db_lo = b_desc0 | (uint64_t)(((sbase + 2 * TILE_BYTES + kk * b_step) >> 4) & 0x3FFF);
+            const uint32_t ta_hi = ta0 + kk * 8, ta_lo = ta0 + BK + kk * 8;
+            const uint32_t accum = (kb | kk) != 0;
+            if (passes == 3) {
+              umma_tf32_ts(tmem_d, ta_lo, db_hi, idesc, accum);
+              umma_tf32_ts(tmem_d, ta_hi, db_lo, idesc, 1);
+              umma_tf32_ts(tmem_d, ta_hi, db_hi, idesc, 1);
+            } else if (passes == 4) {
+              umma_tf32_ts(tmem_d, ta_lo, db_lo, idesc, accum);   // small terms first
+              umma_tf32_ts(tmem_d, ta_lo, db_hi, idesc, 1);
+              umma_tf32_ts(tmem_d, ta_hi, db_lo, idesc, 1);
+              umma_tf32_ts(tmem_d, ta_hi, db_hi, idesc, 1);
             } else {
-              umma_tf32_ts(tmem_d, ta_hi, db_hi, p.idesc, accum);
+              umma_tf32_ts(tmem_d, ta_hi, db_hi, idesc, accum);
             }
-            accum = 1;
           }
-          umma_commit(&empty_bar[stage]);                    // frees the smem stage when the MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&empty_bar[stage]);                    // frees the stage when the MMAs retire
         }
-        umma_commit(&tmem_full[acc]);                        // accumulator complete -> epilogue
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);         // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ============================== epilogue ==============================
