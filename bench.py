@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-eager", action="store_true", help="e2e arm without the CUDA-graph capture")
+    ap.add_argument("--e2e-no-prefetch", action="store_true",
+                    help="e2e arm: H2D copies inside the step's graph instead of prefetching the next step's inputs")
     ap.add_argument("--no-bank", action="store_true")
     ap.add_argument("--cuda-profiler", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
@@ -307,13 +310,29 @@ def run_ours(args):
                 def __len__(self):
                     return len(self.items)
             return float(step(_Lazy(xs), _Lazy(eis)).item())
-        e2e_step()
+        mode = "eager (copy stream + per-snapshot events)"
+        run_step = e2e_step
+        if not args.e2e_eager:
+            # the sync-free step captured once as a CUDA graph: H2D copies, forward, loss, backward, D2H of the loss
+            try:
+                gstep = tagan_b200.GraphedStep(lambda xs, eis: step(xs, eis), xs_h, eis_h, dev,
+                                               prefetch=not args.e2e_no_prefetch)
+                run_step = gstep
+                mode = ("cuda graph (fwd + bwd + D2H loss); every step copies its inputs H2D from pinned memory into a "
+                        "staging set on a copy stream while the previous step's graph runs (loader-style prefetch), "
+                        "then moves them device-to-device into the graph's static inputs"
+                        if not args.e2e_no_prefetch else
+                        "cuda graph (H2D copies + fwd + bwd + D2H loss in one graph launch per step, no prefetch)")
+            except Exception as exc:            # capture unsupported in this environment: measure the eager path
+                mode = "eager (graph capture failed: %s)" % (str(exc).splitlines()[0][:120],)
+                torch.cuda.synchronize()
+        run_step()
         barrier()
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(args.steps):
-            e2e_step()
+            last_loss = run_step()
         g1.record()
         barrier()
         ems = torch.tensor([g0.elapsed_time(g1)], device=dev)
@@ -321,7 +340,7 @@ def run_ours(args):
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": units_per_step / (float(ems.item()) / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": float(ems.item()) / args.steps,
-               "wall_ms_per_step": (time.perf_counter() - t0) / args.steps * 1e3}
+               "wall_ms_per_step": (time.perf_counter() - t0) / args.steps * 1e3, "mode": mode, "loss": last_loss}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on this box's host cores ------------
     cpu = None

@@ -12,7 +12,8 @@ from .layers import (AsymmetricTemporalAttention, GeometricAttention, LayerNorm,
 
 from .memory_bank import NodeMemoryBank  # noqa: F401,E402
 from .model import TAGANLayer, patch  # noqa: F401,E402
+from .graphed import GraphedStep  # noqa: F401,E402
 
-__all__ = ["NodeMemoryBank", "TAGANLayer", "patch", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
+__all__ = ["NodeMemoryBank", "TAGANLayer", "patch", "GraphedStep", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
            "TemporalGRUCell", "TemporalEvolutionLayer", "TemporalSkipConnection", "TemporalGatingUnit",
            "TemporalPropagation"]

@@ -235,3 +235,43 @@ def test_skip_layernorm_module_matches_torch(dev):
     x = torch.randn(500, 128, device=dev)
     ref = torch.nn.functional.layer_norm(x, (128,), ln.weight, ln.bias, 1e-5)
     _close(ln(x).detach(), ref.detach())
+
+
+@pytest.mark.parametrize("prefetch", [False, True])
+def test_graphed_step_matches_eager(prefetch):
+    """GraphedStep (H2D + forward + backward + D2H in one CUDA graph) reproduces the eager step: same loss and the
+    same gradients on every replay, and new host inputs are picked up by the next replay."""
+    import tagan_b200
+    from tagan_b200 import synth
+    dev = torch.device("cuda:0")
+    w = synth.WORKLOADS["c1"]
+    xs_h, eis_h, _ = synth.make_sequence(w, seed=3, pin=True)
+    n, t_steps = w.num_nodes, w.snapshots
+    ts = torch.arange(t_steps, dtype=torch.float32, device=dev).expand(n, t_steps)
+    torch.manual_seed(0)
+    layer = tagan_b200.TAGANLayer(w.hidden, w.heads, "euclidean").to(dev)
+
+    def fn(xs, eis):
+        layer.zero_grad(set_to_none=True)
+        loss = layer(xs, eis, ts).square().mean()
+        loss.backward()
+        return loss
+
+    def eager():
+        loss = fn([x.to(dev) for x in xs_h], [e.to(dev) for e in eis_h])
+        return float(loss), {k: p.grad.clone() for k, p in layer.named_parameters() if p.grad is not None}
+
+    l0, g0 = eager()
+    step = tagan_b200.GraphedStep(fn, xs_h, eis_h, dev, prefetch=prefetch)
+    for _ in range(2):
+        l1 = step()
+        assert abs(l1 - l0) <= 1e-6 * max(1.0, abs(l0)), (l1, l0)
+        for k, p in layer.named_parameters():
+            if k in g0:
+                assert torch.equal(p.grad, g0[k]), k
+    xs_h[0].mul_(1.5)                                   # new host data
+    l2, g2 = eager()
+    if prefetch:                                        # the step after next sees it (the next one was prefetched)
+        assert abs(step() - l0) <= 1e-6 * max(1.0, abs(l0))
+    l3 = step()
+    assert abs(l3 - l2) <= 1e-6 * max(1.0, abs(l2)) and abs(l3 - l0) > 0
