@@ -201,11 +201,15 @@ def run_ours(args):
     from tagan_b200.dist import GradBucket
     bucket = GradBucket(list(layer.parameters())) if world > 1 else None
 
-    def step(xs, eis):
+    def fwd_bwd(xs, eis):
         layer.zero_grad(set_to_none=True)
         out = layer(xs, eis, ts_d, bank=bank, node_ids=[ids] * t_steps)
         loss = out.square().mean()
         loss.backward()
+        return loss
+
+    def step(xs, eis):
+        loss = fwd_bwd(xs, eis)
         if world > 1:                       # data-parallel: one flat NCCL all-reduce of the gradients
             bucket.all_reduce(world)
         return loss
@@ -312,11 +316,12 @@ def run_ours(args):
             return float(step(_Lazy(xs), _Lazy(eis)).item())
         mode = "eager (copy stream + per-snapshot events)"
         run_step = e2e_step
+        gstep = None
         if not args.e2e_eager:
             # the sync-free step captured once as a CUDA graph: H2D copies, forward, loss, backward, D2H of the loss
             try:
-                gstep = tagan_b200.GraphedStep(lambda xs, eis: step(xs, eis), xs_h, eis_h, dev,
-                                               prefetch=not args.e2e_no_prefetch)
+                gstep = tagan_b200.GraphedStep(fwd_bwd, xs_h, eis_h, dev, prefetch=not args.e2e_no_prefetch,
+                                               after_replay=(lambda: bucket.all_reduce(world)) if world > 1 else None)
                 run_step = gstep
                 mode = ("cuda graph (fwd + bwd + D2H loss); every step copies its inputs H2D from pinned memory into a "
                         "staging set on a copy stream while the previous step's graph runs (loader-style prefetch), "
@@ -341,6 +346,9 @@ def run_ours(args):
         e2e = {"value": units_per_step / (float(ems.item()) / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": float(ems.item()) / args.steps,
                "wall_ms_per_step": (time.perf_counter() - t0) / args.steps * 1e3, "mode": mode, "loss": last_loss}
+        if gstep is not None:
+            gstep.release()
+            gstep = run_step = None
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on this box's host cores ------------
     cpu = None
@@ -363,7 +371,10 @@ def run_ours(args):
                            "l2": "inputs larger than L2 (each step streams > 10 GB)"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -52,12 +52,15 @@ class GraphedStep:
 
     def __init__(self, fn: Callable, xs_host: Sequence[torch.Tensor], eis_host: Sequence[torch.Tensor],
                  device: torch.device, warmup: int = 2, prefetch: bool = True,
-                 before_capture: Optional[Callable] = None):
+                 before_capture: Optional[Callable] = None, after_replay: Optional[Callable] = None):
         for t in list(xs_host) + list(eis_host):
             if not t.is_pinned():
                 raise ValueError("GraphedStep: host inputs must be pinned (the graph holds their addresses)")
         self.xs_host, self.eis_host = list(xs_host), list(eis_host)
         self.device, self.prefetch = device, prefetch
+        # eager work enqueued right after every replay (e.g. the data-parallel gradient all-reduce: NCCL collectives
+        # are kept OUT of the captured graph so that communicator teardown never waits on a graph that still holds them)
+        self.after_replay = after_replay
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.xs_host + self.eis_host)
         side = torch.cuda.Stream(device=device)
@@ -131,6 +134,13 @@ class GraphedStep:
             self._issue_prefetch()                                      # next step's inputs, under this step's kernels
         else:
             self.graph.replay()
+        if self.after_replay is not None:
+            self.after_replay()
+
+    def release(self) -> None:
+        """Drop the captured graph and its memory pool (call before tearing down process groups)."""
+        torch.cuda.synchronize(self.device)
+        self.graph.reset()
 
     def __call__(self) -> float:
         self.launch()
