@@ -65,8 +65,8 @@ class GraphedStep:
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.xs_host + self.eis_host)
         side = torch.cuda.Stream(device=device)
         self._copy = copy = torch.cuda.Stream(device=device)
-        self._xs = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in self.xs_host]
-        self._eis = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in self.eis_host]
+        self._xs = self._alloc_like(self.xs_host)
+        self._eis = self._alloc_like(self.eis_host)
 
         def body_with_copies():
             cur = torch.cuda.current_stream()
@@ -112,6 +112,14 @@ class GraphedStep:
         if prefetch:
             self._staged.record(torch.cuda.current_stream())
             self._issue_prefetch()
+
+    def _alloc_like(self, hosts):
+        """Device twins of the host tensors; one allocation sliced per snapshot when the shapes agree, so that the
+        model's ``ops.stack_rows`` is a view."""
+        h0 = hosts[0]
+        if all(h.shape == h0.shape and h.dtype == h0.dtype for h in hosts):
+            return list(torch.empty((len(hosts),) + tuple(h0.shape), dtype=h0.dtype, device=self.device).unbind(0))
+        return [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in hosts]
 
     def _issue_prefetch(self) -> None:
         """H2D copy of the host tensors' current contents into the staging set (copy stream, asynchronous)."""

@@ -80,6 +80,23 @@ class GeometricAttention(nn.Module):
             out = ops.add(o, x)
         return (out, attn) if return_attention_weights else out
 
+    def forward_seq(self, x3: torch.Tensor, csrs) -> torch.Tensor:
+        """The layer over T snapshots of the same N nodes at once: x3 ``[T,N,H]`` -> ``[T,N,H]``.  LN1, the fused QKV
+        projection, the output projection and LN2 run once over all ``T*N`` rows (one large tcgen05 GEMM each instead
+        of T small ones); kernel (a) runs per snapshot on row slices.  Same arithmetic per row as ``forward_csr``."""
+        t_steps, n, hdim = x3.shape
+        rows = x3.reshape(t_steps * n, hdim)
+        ln = self.use_layer_norm
+        xn = ops.layer_norm(rows, self.layer_norm1.weight, self.layer_norm1.bias) if ln else rows
+        w_qkv = torch.cat([self.q_linear.weight, self.k_linear.weight, self.v_linear.weight], 0)
+        b_qkv = torch.cat([self.q_linear.bias, self.k_linear.bias, self.v_linear.bias], 0)
+        qkv = ops.linear(xn, w_qkv, b_qkv)
+        ctx = ops.geo_attention_seq(qkv, csrs, self.num_heads, self.distance_metric, getattr(self, "distance_param", None))
+        o = ops.linear(ctx, self.output_proj.weight, self.output_proj.bias)
+        o = self.output_dropout(o)
+        out = ops.layer_norm(o, self.layer_norm2.weight, self.layer_norm2.bias, res=rows) if ln else ops.add(o, rows)
+        return out.view(t_steps, n, hdim)
+
     def extra_repr(self) -> str:
         return (f"hidden_dim={self.hidden_dim}, num_heads={self.num_heads}, distance_metric={self.distance_metric}, "
                 f"learnable_distance={self.learnable_distance}, use_layer_norm={self.use_layer_norm}, "
@@ -124,6 +141,16 @@ class TAGANGraphAttention(nn.Module):
                        "edge_col": csr.col[:nnz]}
             return out, weights
         return self.geometric_attention.forward_csr(x, csr)
+
+    def forward_seq(self, xs, edge_indices) -> torch.Tensor:
+        """All T snapshots of a sequence over the same N nodes: list of ``[N,H]`` (or ``[T,N,H]``) + T edge lists (or
+        prebuilt CSRs) -> ``[T,N,H]``.  See ``GeometricAttention.forward_seq``."""
+        x3 = xs if isinstance(xs, torch.Tensor) else ops.stack_rows(xs)
+        n = x3.shape[1]
+        csrs = [ei if isinstance(ei, ops.CSR) else
+                ops.build_csr(ei.to(x3.device), n, transpose=torch.is_grad_enabled(), validate=self.validate_indices)
+                for ei in edge_indices]
+        return self.geometric_attention.forward_seq(x3, csrs)
 
     def extra_repr(self) -> str:
         return f"hidden_dim={self.hidden_dim}"
@@ -288,9 +315,13 @@ class AsymmetricTemporalAttention(nn.Module):
 
     # -- forward --------------------------------------------------------------------------
     def forward(self, x, time_stamps: Optional[torch.Tensor] = None, attention_mask=None,
-                return_attention_weights: bool = False):
-        time_major = False
-        if isinstance(x, list):                                       # :928-976
+                return_attention_weights: bool = False, time_major: bool = False):
+        """``time_major=True`` (extension): ``x`` is the physical ``[T,B,H]`` stack of the per-snapshot tensors, i.e.
+        what the list form is turned into anyway -- saves the stack copy; the result is the same ``[B,T,H]`` view."""
+        if time_major and isinstance(x, torch.Tensor):
+            phys = x.contiguous()
+            t, b, hdim = phys.shape
+        elif isinstance(x, list):                                     # :928-976
             cur = [t_[0] if isinstance(t_, list) and len(t_) > 0 else t_ for t_ in x]
             mx = max(t_.shape[0] for t_ in cur)
             cur = [F.pad(t_, (0, 0, 0, mx - t_.shape[0])) if t_.shape[0] < mx else t_ for t_ in cur]
@@ -298,6 +329,7 @@ class AsymmetricTemporalAttention(nn.Module):
             time_major = True
             t, b, hdim = phys.shape
         else:
+            time_major = False
             phys = x.contiguous()
             b, t, hdim = phys.shape
         dev = phys.device

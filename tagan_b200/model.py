@@ -29,17 +29,25 @@ class TAGANLayer(nn.Module):
         # False: the reference's observable behaviour (bank gathered/updated, gating unit unused); True: the intended
         # per-snapshot gating pass (TemporalPropagation.forward_with_memory)
         self.gated_memory = False
+        # batch LN / QKV / out-projection of the geometric layer over all snapshots when they share the node set
+        self.batched_geometric = True
 
     def forward(self, xs: Sequence[torch.Tensor], edge_indices: Sequence, time_stamps: Optional[torch.Tensor] = None,
                 bank: Optional[NodeMemoryBank] = None, node_ids: Optional[Sequence[torch.Tensor]] = None):
         """xs: T tensors ``[N,H]``; edge_indices: T ``[2,E]`` int64 tensors (or prebuilt ``ops.CSR``);
         time_stamps ``[N,T]``.  Returns ``[N,T,H]``."""
-        geo = [self.geometric(x, ei) for x, ei in zip(xs, edge_indices)]
+        xs_l = list(xs)
+        uniform = all(isinstance(x, torch.Tensor) and x.shape == xs_l[0].shape for x in xs_l)
+        if uniform and self.batched_geometric:
+            # same node set in every snapshot: LN / projections of the geometric layer batched over T (one GEMM each)
+            geo = self.geometric.forward_seq(xs_l, edge_indices)                      # [T,N,H]
+        else:
+            geo = [self.geometric(x, ei) for x, ei in zip(xs_l, edge_indices)]
         if bank is not None and self.gated_memory:
             n = geo[0].shape[0]
             ids_seq = node_ids if node_ids is not None else [torch.arange(n, dtype=torch.int32, device=geo[0].device)] * len(geo)
             prop = self.propagation.forward_with_memory(geo, ids_seq, bank, time_stamps)
-            return self.temporal_attention(list(prop.unbind(0)), time_stamps=time_stamps)
+            return self.temporal_attention(prop, time_stamps=time_stamps, time_major=True)
         prop = self.propagation.forward_core(geo, time_stamps)                      # [T,N,H]
         if bank is not None:
             t_steps, n = prop.shape[0], prop.shape[1]
@@ -47,7 +55,7 @@ class TAGANLayer(nn.Module):
                 ids = node_ids[t] if node_ids is not None else torch.arange(n, dtype=torch.int32, device=prop.device)
                 bank.get_states(ids)                                                 # previous states (gather)
                 bank.update(ids, prop[t].detach(), t)                                # scatter-update / decay / prune
-        return self.temporal_attention(list(prop.unbind(0)), time_stamps=time_stamps)
+        return self.temporal_attention(prop, time_stamps=time_stamps, time_major=True)
 
 
 def patch(model: nn.Module) -> nn.Module:

@@ -329,6 +329,92 @@ def geo_attention_core(qkv, csr: CSR, heads: int, metric: str, metric_param=None
     return _GeoAttnFn.apply(qkv, metric_param, csr, heads, METRIC_ID[metric], want_attn)
 
 
+class _GeoAttnSeqFn(torch.autograd.Function):
+    """Kernel (a) over T snapshots that share one stacked projection ``qkv [T*N,3H]``: one launch pair per
+    snapshot on row slices, one autograd node for the whole stage."""
+
+    @staticmethod
+    def forward(ctx, qkv, metric_param, csrs, heads: int, metric: int):
+        lib = _lib.load()
+        qkv2, rows, three_h, ld = _rows(qkv)
+        t_steps = len(csrs)
+        n = csrs[0].num_nodes
+        if rows != t_steps * n or any(c.num_nodes != n for c in csrs):
+            raise ValueError("geo_attention_seq: qkv rows must be T * N with the same N in every snapshot")
+        h = three_h // 3
+        ctxv = torch.empty(rows, h, dtype=torch.float32, device=qkv.device)
+        lse = torch.empty(rows, heads, dtype=torch.float32, device=qkv.device)
+        base, cbase, lbase = qkv2.data_ptr(), ctxv.data_ptr(), lse.data_ptr()
+        for t, csr in enumerate(csrs):
+            off = base + t * n * ld * 4
+            q, k, v = (C.c_void_p(off + i * h * 4) for i in range(3))
+            with _timed("geo_attn_fwd"):
+                rc = lib.tagan_geo_attn_fwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), n, h, heads, metric,
+                                            _ptr(metric_param), C.c_void_p(cbase + t * n * h * 4),
+                                            C.c_void_p(lbase + t * n * heads * 4), None, _stream())
+            _lib.check(rc, "tagan_geo_attn_fwd")
+        CALLS["n"] += t_steps
+        ctx.save_for_backward(qkv2, metric_param, ctxv, lse)
+        ctx.csrs, ctx.heads, ctx.metric = csrs, heads, metric
+        return ctxv
+
+    @staticmethod
+    def backward(ctx, dctx):
+        lib = _lib.load()
+        qkv2, metric_param, ctxv, lse = ctx.saved_tensors
+        csrs, heads, metric = ctx.csrs, ctx.heads, ctx.metric
+        if any(c.rowptr_t is None for c in csrs):
+            raise RuntimeError("CSR was built without its transpose; backward needs it")
+        rows, three_h = qkv2.shape
+        h = three_h // 3
+        t_steps = len(csrs)
+        n = csrs[0].num_nodes
+        ld = qkv2.stride(0) if rows > 1 else three_h
+        dev = dctx.device
+        dctx = _f32c(dctx).contiguous()
+        dqkv = torch.empty(rows, three_h, dtype=torch.float32, device=dev)
+        delta = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        want_dp = metric_param is not None and metric in (7, 8)
+        dp_ws = torch.empty(n, heads, dtype=torch.float32, device=dev) if want_dp else None
+        dparam_t = torch.empty(t_steps, heads, dtype=torch.float32, device=dev) if want_dp else None
+        base, dbase = qkv2.data_ptr(), dqkv.data_ptr()
+        for t, csr in enumerate(csrs):
+            off, doff = base + t * n * ld * 4, dbase + t * n * three_h * 4
+            q, k, v = (C.c_void_p(off + i * h * 4) for i in range(3))
+            dq, dk, dv = (C.c_void_p(doff + i * h * 4) for i in range(3))
+            with _timed("geo_attn_bwd"):
+                rc = lib.tagan_geo_attn_bwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.rowptr_t), _ptr(csr.row_t),
+                                            n, h, heads, metric, _ptr(metric_param),
+                                            C.c_void_p(ctxv.data_ptr() + t * n * h * 4),
+                                            C.c_void_p(lse.data_ptr() + t * n * heads * 4),
+                                            C.c_void_p(dctx.data_ptr() + t * n * h * 4), dq, dk, dv, three_h, _ptr(delta),
+                                            _ptr(dp_ws), C.c_void_p(dparam_t.data_ptr() + t * heads * 4) if want_dp else None,
+                                            _stream())
+            _lib.check(rc, "tagan_geo_attn_bwd")
+        CALLS["n"] += (3 if want_dp else 2) * t_steps
+        dparam = dparam_t.sum(0) if want_dp else None
+        return dqkv, dparam, None, None, None
+
+
+def geo_attention_seq(qkv, csrs, heads: int, metric: str, metric_param=None):
+    """qkv ``[T*N,3H]`` (stacked fused projection) + T CSRs over the same N nodes -> ctx ``[T*N,H]``."""
+    return _GeoAttnSeqFn.apply(qkv, metric_param, list(csrs), heads, METRIC_ID[metric])
+
+
+def stack_rows(xs) -> torch.Tensor:
+    """``torch.stack(xs, 0)`` that costs nothing when the tensors already are consecutive slices of one
+    allocation (what ``GraphedStep`` hands out) and none of them carries a gradient."""
+    xs = list(xs)
+    x0 = xs[0]
+    if isinstance(x0, torch.Tensor) and x0.is_contiguous() and not any(x.requires_grad for x in xs):
+        numel, base, off0 = x0.numel(), x0.untyped_storage().data_ptr(), x0.storage_offset()
+        if numel and all(x.shape == x0.shape and x.dtype == x0.dtype and x.is_contiguous()
+                         and x.untyped_storage().data_ptr() == base and x.storage_offset() == off0 + i * numel
+                         for i, x in enumerate(xs)):
+            return torch.as_strided(x0, (len(xs),) + tuple(x0.shape), (numel,) + tuple(x0.stride()), off0)
+    return torch.stack(xs, 0)
+
+
 # ----------------------------------------------------------------------------------------
 # element-wise helpers
 # ----------------------------------------------------------------------------------------
