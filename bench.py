@@ -203,8 +203,10 @@ def run_ours(args):
 
     def fwd_bwd(xs, eis):
         layer.zero_grad(set_to_none=True)
-        out = layer(xs, eis, ts_d, bank=bank, node_ids=[ids] * t_steps)
-        loss = out.square().mean()
+        out = layer(xs, eis, ts_d, bank=bank, node_ids=[ids] * t_steps)       # [N,T,H] view of time-major storage
+        # mean of squares, taken in the storage order of `out` (a permutation of the same elements) so that the
+        # loss and its gradient are contiguous element-wise passes instead of strided ones
+        loss = out.permute(1, 0, 2).square().mean()
         loss.backward()
         return loss
 
