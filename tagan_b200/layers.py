@@ -147,9 +147,12 @@ class TAGANGraphAttention(nn.Module):
         prebuilt CSRs) -> ``[T,N,H]``.  See ``GeometricAttention.forward_seq``."""
         x3 = xs if isinstance(xs, torch.Tensor) else ops.stack_rows(xs)
         n = x3.shape[1]
-        csrs = [ei if isinstance(ei, ops.CSR) else
-                ops.build_csr(ei.to(x3.device), n, transpose=torch.is_grad_enabled(), validate=self.validate_indices)
-                for ei in edge_indices]
+        if self.validate_indices:                         # validation reads a status word on the host: build in line
+            csrs = [ei if isinstance(ei, ops.CSR) else
+                    ops.build_csr(ei.to(x3.device), n, transpose=torch.is_grad_enabled(), validate=True)
+                    for ei in edge_indices]
+        else:                                             # sync-free: build on the side stream, under LN1 + QKV
+            csrs = ops.build_csr_async(edge_indices, n, x3.device, transpose=torch.is_grad_enabled())
         return self.geometric_attention.forward_seq(x3, csrs)
 
     def extra_repr(self) -> str:

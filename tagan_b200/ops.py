@@ -108,6 +108,7 @@ class CSR:
     row_t: Optional[torch.Tensor]
     perm_t: Optional[torch.Tensor]
     status: torch.Tensor
+    ready: Optional[torch.cuda.Event] = None    # set when the CSR was built on a side stream (see build_csr_async)
 
     @property
     def nnz(self) -> int:          # host sync; only for tests / attention-weight export
@@ -146,6 +147,46 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int, transpose: bool = True, 
     if validate and int(status.item()) != 0:
         raise IndexError("edge_index out of range for num_nodes=%d" % num_nodes)
     return CSR(num_nodes, e, rowptr, col, row, rowptr_t, row_t, perm_t, status)
+
+
+_SIDE = {}
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    """One auxiliary stream per device for work that is independent of the main chain (CSR builds)."""
+    idx = torch.device(device).index
+    st = _SIDE.get(idx)
+    if st is None:
+        st = _SIDE[idx] = torch.cuda.Stream(device=device)
+    return st
+
+
+def build_csr_async(edge_indices, num_nodes: int, device, transpose: bool = True, validate: bool = False):
+    """Build the CSRs of several snapshots on the side stream.  They depend only on ``edge_index``, so they run under
+    whatever the main stream does next (LN1 + QKV projection of the batched geometric stage, then the attention of
+    earlier snapshots); each CSR carries a ``ready`` event that its consumer waits for."""
+    main = torch.cuda.current_stream()
+    side = side_stream(device)
+    side.wait_stream(main)
+    out = []
+    with torch.cuda.stream(side):
+        for ei in edge_indices:
+            if isinstance(ei, CSR):
+                out.append(ei)
+                continue
+            csr = build_csr(ei.to(device), num_nodes, transpose=transpose, validate=validate)
+            for t in (csr.rowptr, csr.col, csr.row, csr.rowptr_t, csr.row_t, csr.perm_t, csr.status):
+                if t is not None:
+                    t.record_stream(main)
+            csr.ready = torch.cuda.Event()
+            csr.ready.record(side)
+            out.append(csr)
+    return out
+
+
+def wait_csr(csr: CSR) -> None:
+    if csr.ready is not None:
+        torch.cuda.current_stream().wait_event(csr.ready)
 
 
 # ----------------------------------------------------------------------------------------
@@ -348,6 +389,7 @@ class _GeoAttnSeqFn(torch.autograd.Function):
         for t, csr in enumerate(csrs):
             off = base + t * n * ld * 4
             q, k, v = (C.c_void_p(off + i * h * 4) for i in range(3))
+            wait_csr(csr)
             with _timed("geo_attn_fwd"):
                 rc = lib.tagan_geo_attn_fwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), n, h, heads, metric,
                                             _ptr(metric_param), C.c_void_p(cbase + t * n * h * 4),
