@@ -348,7 +348,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       tc_fence_after();
       float* out = p.partial ? p.partial + (int64_t)ks * p.M * p.N : p.C;
       const int64_t ldo = p.partial ? p.N : p.ldc;
-      const bool interior = p.c_vec && ((int64_t)(mt + 1) * BM <= p.M) && (n0 + BN <= p.N) && !(p.partial == nullptr && p.accumulate);
+      const bool interior = p.c_vec && ((int64_t)(mt + 1) * BM <= p.M) && (n0 + BN <= p.N);
+      const bool rmw = p.partial == nullptr && p.accumulate;                  // C += A.B (the GRU scan's per-step GEMMs)
       const bool bias_vec = p.partial == nullptr && p.bias != nullptr;       // host guarantees 16-byte alignment when c_vec
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
@@ -388,6 +389,13 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = lds128(src0 + (uint32_t)(i * 4 * EPI_PITCH * 4));
           float* orow = out + ((int64_t)mt * BM + warp * 32 + (lane >> 3)) * ldo + c0;
+          if (rmw) {
+            float4 o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = *reinterpret_cast<const float4*>(orow + (int64_t)(i * 4) * ldo);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x += o[i].x; v[i].y += o[i].y; v[i].z += o[i].z; v[i].w += o[i].w; }
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
