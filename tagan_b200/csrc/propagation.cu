@@ -79,6 +79,91 @@ __global__ void blend_bwd_kernel(const float* __restrict__ dout, const float* __
   *o = accumulate ? *o + v : v;
 }
 
+// ---- float4 forms of the four kernels above (H, every leading dimension and every base pointer 16-byte aligned):
+// same per-element arithmetic, one 128-bit access per tensor per thread.
+#define V4_OP(dst, expr)                                                       \
+  { float4 _o; { const int q = 0; _o.x = (expr); } { const int q = 1; _o.y = (expr); } \
+    { const int q = 2; _o.z = (expr); } { const int q = 3; _o.w = (expr); } dst = _o; }
+__device__ __forceinline__ float f4(const float4& v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__global__ void gates_fwd_vec_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ second, int64_t lds,
+                                     float* __restrict__ r, float* __restrict__ z, float* __restrict__ rs, int64_t ldrs,
+                                     int64_t rows, int H4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H4) return;
+  const int64_t row = i / H4;
+  const int c = (int)(i - row * H4) * 4, H = H4 * 4;
+  const float4 gr = ld4(g + row * ldg + c), gz = ld4(g + row * ldg + H + c), sv = ld4(second + row * lds + c);
+  float4 rv, zv, o;
+  V4_OP(rv, sigmoidf_(f4(gr, q)));
+  V4_OP(zv, sigmoidf_(f4(gz, q)));
+  V4_OP(o, f4(rv, q) * f4(sv, q));
+  st4(r + row * H + c, rv);
+  st4(z + row * H + c, zv);
+  st4(rs + row * ldrs + c, o);
+}
+
+__global__ void gates_bwd_vec_kernel(const float* __restrict__ drs, int64_t lddrs, const float* __restrict__ dz,
+                                     const float* __restrict__ r, const float* __restrict__ z,
+                                     const float* __restrict__ second, int64_t lds, float* __restrict__ dg, int64_t lddg,
+                                     float* __restrict__ dsecond, int64_t ldds, int accumulate, int64_t rows, int H4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H4) return;
+  const int64_t row = i / H4;
+  const int c = (int)(i - row * H4) * 4, H = H4 * 4;
+  const float4 rv = ld4(r + row * H + c), zv = ld4(z + row * H + c), d = ld4(drs + row * lddrs + c);
+  const float4 sv = ld4(second + row * lds + c), dzv = ld4(dz + row * H + c);
+  float4 a, b, v;
+  V4_OP(a, f4(d, q) * f4(sv, q) * f4(rv, q) * (1.f - f4(rv, q)));
+  V4_OP(b, f4(dzv, q) * f4(zv, q) * (1.f - f4(zv, q)));
+  st4(dg + row * lddg + c, a);
+  st4(dg + row * lddg + H + c, b);
+  float* o = dsecond + row * ldds + c;
+  if (accumulate) { const float4 old = ld4(o); V4_OP(v, f4(old, q) + f4(d, q) * f4(rv, q)); }
+  else V4_OP(v, f4(d, q) * f4(rv, q));
+  st4(o, v);
+}
+
+__global__ void blend_fwd_vec_kernel(const float* __restrict__ cpre, int64_t ldc, const float* __restrict__ z,
+                                     const float* __restrict__ base, int64_t ldb, float* __restrict__ cand,
+                                     float* __restrict__ out, int residual, int64_t rows, int H4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H4) return;
+  const int64_t row = i / H4;
+  const int c = (int)(i - row * H4) * 4, H = H4 * 4;
+  const float4 cp = ld4(cpre + row * ldc + c), zv = ld4(z + row * H + c), b = ld4(base + row * ldb + c);
+  float4 t, o;
+  V4_OP(t, tanhf(f4(cp, q)));
+  if (residual) V4_OP(o, ((1.f - f4(zv, q)) * f4(b, q) + f4(zv, q) * f4(t, q)) + f4(b, q))
+  else V4_OP(o, (1.f - f4(zv, q)) * f4(b, q) + f4(zv, q) * f4(t, q))
+  st4(cand + row * H + c, t);
+  st4(out + row * H + c, o);
+}
+
+__global__ void blend_bwd_vec_kernel(const float* __restrict__ dout, const float* __restrict__ z,
+                                     const float* __restrict__ cand, const float* __restrict__ base, int64_t ldb,
+                                     float* __restrict__ dcpre, int64_t lddc, float* __restrict__ dz, float* __restrict__ dbase,
+                                     int64_t lddb, int accumulate, int residual, int64_t rows, int H4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H4) return;
+  const int64_t row = i / H4;
+  const int c = (int)(i - row * H4) * 4, H = H4 * 4;
+  const float4 d = ld4(dout + row * H + c), zv = ld4(z + row * H + c), t = ld4(cand + row * H + c), b = ld4(base + row * ldb + c);
+  float4 a, e, v;
+  V4_OP(a, f4(d, q) * f4(zv, q) * (1.f - f4(t, q) * f4(t, q)));
+  V4_OP(e, f4(d, q) * (f4(t, q) - f4(b, q)));
+  st4(dcpre + row * lddc + c, a);
+  st4(dz + row * H + c, e);
+  float* o = dbase + row * lddb + c;
+  if (accumulate) { const float4 old = ld4(o); V4_OP(v, f4(old, q) + (f4(d, q) * (1.f - f4(zv, q)) + (residual ? f4(d, q) : 0.f))); }
+  else V4_OP(v, f4(d, q) * (1.f - f4(zv, q)) + (residual ? f4(d, q) : 0.f));
+  st4(o, v);
+}
+
+__host__ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // g[t] = agg over u in [max(0,t-w), min(T,t+w+1)) of p[u]; p is [T, inner] (inner = rows*H).
 // A thread walks t for one float4 column so the re-reads of the window hit L1/L2.
 __global__ void window_fwd_kernel(const float* __restrict__ p, float* __restrict__ out, int T, int64_t inner4,
@@ -143,7 +228,10 @@ TAGAN_API int tagan_gates_fwd(const float* g, int64_t ldg, const float* second, 
                               float* rs, int64_t ldrs, int64_t rows, int32_t H, tagan_stream_t stream) {
   if (!g || !second || !r || !z || !rs || rows < 0 || H <= 0 || ldg < 2 * H) return TAGAN_E_INVALID;
   if (rows == 0) return 0;
-  gates_fwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(g, ldg, second, lds, r, z, rs, ldrs, rows, H);
+  if (H % 4 == 0 && ldg % 4 == 0 && lds % 4 == 0 && ldrs % 4 == 0 && al16(g) && al16(second) && al16(r) && al16(z) && al16(rs))
+    gates_fwd_vec_kernel<<<ceil_div_i64(rows * (H / 4), 256), 256, 0, as_stream(stream)>>>(g, ldg, second, lds, r, z, rs, ldrs, rows, H / 4);
+  else
+    gates_fwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(g, ldg, second, lds, r, z, rs, ldrs, rows, H);
   return tagan_launch_status();
 }
 
@@ -152,8 +240,13 @@ TAGAN_API int tagan_gates_bwd(const float* drs, int64_t lddrs, const float* dz, 
                               int64_t ldds, int32_t accumulate, int64_t rows, int32_t H, tagan_stream_t stream) {
   if (!drs || !dz || !r || !z || !second || !dg || !dsecond || rows < 0 || H <= 0 || lddg < 2 * H) return TAGAN_E_INVALID;
   if (rows == 0) return 0;
-  gates_bwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(drs, lddrs, dz, r, z, second, lds, dg,
-                                                                               lddg, dsecond, ldds, accumulate, rows, H);
+  if (H % 4 == 0 && lddrs % 4 == 0 && lds % 4 == 0 && lddg % 4 == 0 && ldds % 4 == 0 && al16(drs) && al16(dz) && al16(r) &&
+      al16(z) && al16(second) && al16(dg) && al16(dsecond))
+    gates_bwd_vec_kernel<<<ceil_div_i64(rows * (H / 4), 256), 256, 0, as_stream(stream)>>>(drs, lddrs, dz, r, z, second, lds, dg,
+                                                                                         lddg, dsecond, ldds, accumulate, rows, H / 4);
+  else
+    gates_bwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(drs, lddrs, dz, r, z, second, lds, dg,
+                                                                                 lddg, dsecond, ldds, accumulate, rows, H);
   return tagan_launch_status();
 }
 
@@ -162,8 +255,12 @@ TAGAN_API int tagan_blend_fwd(const float* cand_pre, int64_t ldc, const float* z
                               tagan_stream_t stream) {
   if (!cand_pre || !z || !base || !cand || !out || rows < 0 || H <= 0 || ldc < H) return TAGAN_E_INVALID;
   if (rows == 0) return 0;
-  blend_fwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(cand_pre, ldc, z, base, ldb, cand, out,
-                                                                               residual, rows, H);
+  if (H % 4 == 0 && ldc % 4 == 0 && ldb % 4 == 0 && al16(cand_pre) && al16(z) && al16(base) && al16(cand) && al16(out))
+    blend_fwd_vec_kernel<<<ceil_div_i64(rows * (H / 4), 256), 256, 0, as_stream(stream)>>>(cand_pre, ldc, z, base, ldb, cand, out,
+                                                                                         residual, rows, H / 4);
+  else
+    blend_fwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(cand_pre, ldc, z, base, ldb, cand, out,
+                                                                                 residual, rows, H);
   return tagan_launch_status();
 }
 
@@ -172,8 +269,13 @@ TAGAN_API int tagan_blend_bwd(const float* dout, const float* z, const float* ca
                               int32_t accumulate, int32_t residual, int64_t rows, int32_t H, tagan_stream_t stream) {
   if (!dout || !z || !cand || !base || !dcand_pre || !dz || !dbase || rows < 0 || H <= 0 || lddc < H) return TAGAN_E_INVALID;
   if (rows == 0) return 0;
-  blend_bwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(dout, z, cand, base, ldb, dcand_pre, lddc,
-                                                                               dz, dbase, lddb, accumulate, residual, rows, H);
+  if (H % 4 == 0 && ldb % 4 == 0 && lddc % 4 == 0 && lddb % 4 == 0 && al16(dout) && al16(z) && al16(cand) && al16(base) &&
+      al16(dcand_pre) && al16(dz) && al16(dbase))
+    blend_bwd_vec_kernel<<<ceil_div_i64(rows * (H / 4), 256), 256, 0, as_stream(stream)>>>(dout, z, cand, base, ldb, dcand_pre, lddc,
+                                                                                         dz, dbase, lddb, accumulate, residual, rows, H / 4);
+  else
+    blend_bwd_kernel<<<ceil_div_i64(rows * H, 256), 256, 0, as_stream(stream)>>>(dout, z, cand, base, ldb, dcand_pre, lddc,
+                                                                                 dz, dbase, lddb, accumulate, residual, rows, H);
   return tagan_launch_status();
 }
 
