@@ -105,6 +105,7 @@ class GeometricAttention(nn.Module):
 
 class TAGANGraphAttention(nn.Module):
     """Mirror of reference ``TAGANGraphAttention`` (src/tagan/layers/graph_attention.py:15-136).
+    ``edge_index=None`` (the reference's unmasked all-pairs mode) is served up to ``MAX_DENSE_NODES`` nodes.
 
     ``forward(x, edge_index, edge_attr=None, return_attention_weights=False)`` has the
     reference's signature.  ``edge_attr`` is accepted and ignored exactly as in the reference
@@ -124,14 +125,21 @@ class TAGANGraphAttention(nn.Module):
                                                       use_layer_norm, learnable_distance)
         self.validate_indices = True
 
+    MAX_DENSE_NODES = 4096
+
     def forward(self, x, edge_index, edge_attr=None, return_attention_weights: bool = False):
         if isinstance(edge_index, ops.CSR):
             csr = edge_index
         else:
             if edge_index is None:
-                # the reference then attends over ALL node pairs (no mask, graph_attention.py:95-96);
-                # that dense O(N^2) mode is out of scope for the sparse kernel
-                raise NotImplementedError("edge_index=None (dense all-pairs attention) is not supported")
+                # the reference then attends over ALL node pairs (no mask, graph_attention.py:95-96).  Served by the
+                # same kernel on the complete graph while that is small; the O(N^2) mode has no use beyond toy sizes
+                n = x.shape[0]
+                if n > self.MAX_DENSE_NODES:
+                    raise NotImplementedError(f"edge_index=None (dense all-pairs attention) is supported up to "
+                                              f"{self.MAX_DENSE_NODES} nodes, got {n}")
+                ar = torch.arange(n, device=x.device)
+                edge_index = torch.stack([ar.repeat_interleave(n), ar.repeat(n)], 0)
             csr = ops.build_csr(edge_index.to(x.device), x.shape[0], transpose=torch.is_grad_enabled(),
                                 validate=self.validate_indices)
         if return_attention_weights:

@@ -213,6 +213,41 @@ def test_geo_attention_vs_oracle_shapes(dev, hidden, heads, metric):
         torch.testing.assert_close(p.grad.cpu(), gref, **tol, msg=lambda m, k=k: f"d{k}: {m}")
 
 
+@pytest.mark.parametrize("metric", ["scaled_dot_product", "euclidean"])
+def test_geo_attention_without_edge_index_is_dense_all_pairs(dev, metric):
+    """``edge_index=None``: the reference applies no mask (graph_attention.py:95-96), i.e. plain dense attention over
+    all node pairs -- compared here with a dense fp32 torch computation of exactly that, and refused beyond the
+    documented size limit."""
+    import tagan_b200
+    torch.manual_seed(11)
+    n, hidden, heads = 300, 64, 4
+    d = hidden // heads
+    layer = tagan_b200.TAGANGraphAttention(hidden, heads, dropout=0.0, distance_metric=metric).to(dev)
+    ga = layer.geometric_attention
+    x = (torch.randn(n, hidden) * 0.5).to(dev).requires_grad_(True)
+    out = layer(x, None)
+    # dense torch reference
+    xr = x.detach().clone().requires_grad_(True)
+    xn = torch.nn.functional.layer_norm(xr, (hidden,), ga.layer_norm1.weight, ga.layer_norm1.bias, 1e-5)
+    q = torch.nn.functional.linear(xn, ga.q_linear.weight, ga.q_linear.bias).view(n, heads, d).transpose(0, 1)
+    k = torch.nn.functional.linear(xn, ga.k_linear.weight, ga.k_linear.bias).view(n, heads, d).transpose(0, 1)
+    v = torch.nn.functional.linear(xn, ga.v_linear.weight, ga.v_linear.bias).view(n, heads, d).transpose(0, 1)
+    if metric == "scaled_dot_product":
+        sc = q @ k.transpose(1, 2) / d ** 0.5
+    else:
+        sc = -torch.sqrt(((q[:, :, None, :] - k[:, None, :, :]) ** 2).sum(-1) + 1e-8)
+    ctx = (torch.softmax(sc, -1) @ v).transpose(0, 1).reshape(n, hidden)
+    o = torch.nn.functional.linear(ctx, ga.output_proj.weight, ga.output_proj.bias)
+    ref = torch.nn.functional.layer_norm(o + xr, (hidden,), ga.layer_norm2.weight, ga.layer_norm2.bias, 1e-5)
+    _close(out.detach().cpu(), ref.detach().cpu())
+    wout = torch.randn(n, hidden, device=dev)
+    gx, = torch.autograd.grad((out * wout).sum(), x)
+    gr, = torch.autograd.grad((ref * wout).sum(), xr)
+    _close(gx.cpu(), gr.cpu())
+    with pytest.raises(NotImplementedError):
+        layer(torch.zeros(layer.MAX_DENSE_NODES + 1, hidden, device=dev), None)
+
+
 @pytest.mark.parametrize("metric", ["euclidean", "scaled_dot_product", "rbf_kernel"])
 def test_geo_attention_hub_rows_and_columns(dev, metric):
     """Power-law corner: a destination row with ~3000 entries and a source column with ~2500 entries take the
