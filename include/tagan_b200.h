@@ -166,6 +166,13 @@ int tagan_gemm(int32_t op /*0=NT,1=NN,2=TN*/, int64_t m, int64_t n, int64_t k,
                const float* A, int64_t lda, const float* B, int64_t ldb,
                const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t precision,
                void* workspace, size_t workspace_bytes, tagan_stream_t stream);
+/* nn.Linear backward in one call (autograd of the reference's `nn.Linear`s): C[M,N] = A[Kd,M]^T . B[Kd,N] (= dW for
+ * A = dY, B = X) and colsum_a[M] = sum over the Kd rows of A (= db).  On the tensor-core path the column sums are
+ * accumulated while A is split, so the bias gradient needs no second pass over dY. */
+size_t tagan_gemm_tn_colsum_workspace_bytes(int64_t m, int64_t n, int64_t k);
+int tagan_gemm_tn_colsum(int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* B, int64_t ldb,
+                         float* C, int64_t ldc, float* colsum_a, int32_t precision,
+                         void* workspace, size_t workspace_bytes, tagan_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * (b1,b2) per-node temporal attention over the snapshot axis.

@@ -42,6 +42,8 @@ SIGNATURES = {
     "tagan_colsum": (_i32, [_p, _i64, _p, _p, _sz, _i64, _i32, _p]),
     "tagan_gemm_workspace_bytes": (_sz, [_i32, _i64, _i64, _i64]),
     "tagan_gemm": (_i32, [_i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _sz, _p]),
+    "tagan_gemm_tn_colsum_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "tagan_gemm_tn_colsum": (_i32, [_i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _sz, _p]),
     "tagan_tattn_fwd": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _i64, _p, _i32, _f32, _p,
                                _p, _i32, _i32, _p, _p, _p, _p]),
     "tagan_tattn_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),

@@ -14,9 +14,10 @@ int tagan_gemm_tc(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, i
 
 bool tagan_gemm_tma_supported(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb);
 size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K);
+size_t tagan_gemm_tma_colsum_bytes(int64_t M, int64_t N, int64_t K);
 int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                    int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st);
+                   void* workspace, size_t workspace_bytes, cudaStream_t st, float* colsum_a);
 
 TAGAN_API size_t tagan_gemm_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k) {
   if (op < 0 || op > 2 || m < 0 || n < 0 || k < 0) return 0;
@@ -38,12 +39,40 @@ TAGAN_API int tagan_gemm(int32_t op, int64_t m, int64_t n, int64_t k, const floa
     // precision bit 2 (value 4) forces the LDG-fed kernel (used by the tests to cover both tensor-core paths)
     if (!(precision & 4) && tagan_gemm_tma_supported(m, n, k, A, lda, B, ldb))
       return tagan_gemm_tma(op, m, n, k, A, lda, B, ldb, bias, C, ldc, accumulate, passes, workspace, workspace_bytes,
-                            as_stream(stream));
+                            as_stream(stream), nullptr);
     return tagan_gemm_tc(op, m, n, k, A, lda, B, ldb, bias, C, ldc, accumulate, passes, workspace, workspace_bytes,
                          as_stream(stream));
   }
   return tagan_gemm_simt(op, m, n, k, A, lda, B, ldb, bias, C, ldc, accumulate, workspace, workspace_bytes,
                          as_stream(stream));
+}
+
+// dW = A^T . B together with colsum(A) (Linear backward: A = dY [rows, out], B = X [rows, in]; colsum(A) = db).
+// On the TMA-fed tensor-core path the column sums are accumulated by the warps that split A anyway, so the bias
+// gradient costs no second pass over dY; otherwise it is tagan_gemm followed by tagan_colsum.
+TAGAN_API size_t tagan_gemm_tn_colsum_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+  if (m < 0 || n < 0 || k < 0) return 0;
+  size_t a = tagan_gemm_workspace_bytes(2, m, n, k) + tagan_gemm_tma_colsum_bytes(m, n, k);
+  size_t b = tagan_colsum_workspace_bytes(k, (int32_t)m);
+  return a > b ? a : b;
+}
+
+TAGAN_API int tagan_gemm_tn_colsum(int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* B, int64_t ldb,
+                                   float* C, int64_t ldc, float* colsum_a, int32_t precision, void* workspace,
+                                   size_t workspace_bytes, tagan_stream_t stream) {
+  if (m < 0 || n < 0 || k < 0 || !C || !colsum_a || (k > 0 && (!A || !B))) return TAGAN_E_INVALID;
+  if (precision < 0 || precision > 7 || m >= (1LL << 31)) return TAGAN_E_INVALID;
+  if (m == 0) return 0;
+  if (n > 0 && precision > 0 && k > 0 && m * n >= 64 * 64 && !(precision & 4) && tagan_gemm_tma_supported(m, n, k, A, lda, B, ldb)) {
+    const int passes = (precision & 3) == 1 ? 3 : ((precision & 3) == 3 ? 4 : 1);
+    return tagan_gemm_tma(2, m, n, k, A, lda, B, ldb, nullptr, C, ldc, 0, passes, workspace, workspace_bytes,
+                          as_stream(stream), colsum_a);
+  }
+  if (n > 0) {
+    int rc = tagan_gemm(2, m, n, k, A, lda, B, ldb, nullptr, C, ldc, 0, precision, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  return tagan_colsum(A, lda, colsum_a, workspace, workspace_bytes, k, (int32_t)m, stream);
 }
 
 TAGAN_API int tagan_abi_version(void) { return 1; }

@@ -138,6 +138,7 @@ struct Params {
   int passes;              // 4: lo.lo + lo.hi + hi.lo + hi.hi, 3: without lo.lo, 1: plain TF32
   int b_presplit;          // B arrives already split (tmB = hi image, tmB2 = lo image): only A is split in-kernel
   uint32_t idesc;
+  float* colsum_part;       // TN only: [splits][2][M] partial column sums of A (the bias gradient), or null
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -222,6 +223,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
       const int64_t kbeg = (int64_t)ks * p.k_per_split;
       const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
+      float csum = 0.f;                                      // this thread's row of A summed over its k-columns
       for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
         mbar_wait(&raw_bar[stage], phase);                   // TMA bytes have landed
         const uint32_t st_u32 = smem_u32(smem + (size_t)stage * STAGE_BYTES);
@@ -251,6 +253,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
               const float h = tf32_rn(x);
               hi[kk] = __float_as_uint(h);
               lo[kk] = __float_as_uint(tf32_rn(x - h));
+              csum += x;
             }
           }
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
@@ -276,6 +279,12 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (p.colsum_part != nullptr) {                        // bias gradient for free: A has just been read anyway
+        const int nt = (int)(w % p.tiles_n);
+        const int mt = (int)((w / p.tiles_n) % p.tiles_m);
+        const int64_t m = (int64_t)mt * BM + (warp & 3) * 32 + lane;
+        if (nt == 0 && m < p.M) p.colsum_part[((int64_t)ks * 2 + ((warp - SPLIT_WARP0) >> 2)) * p.M + m] = csum;
       }
     }
   } else if (warp == MMA_WARP) {
@@ -460,6 +469,15 @@ __global__ void tma_splitk_reduce(const float* __restrict__ partial, int parts, 
   *o = accumulate ? *o + s : s;
 }
 
+// out[m] = sum over the [parts] partial rows in ascending order (fixed => deterministic)
+__global__ void colsum_parts_reduce(const float* __restrict__ part, int parts, int64_t M, float* __restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float s = 0.f;
+  for (int j = 0; j < parts; ++j) s += part[(int64_t)j * M + m];
+  out[m] = s;
+}
+
 struct Plan { int tiles_m, tiles_n, splits; int64_t k_per_split; };
 Plan make_plan(int64_t M, int64_t N, int64_t K) {
   Plan pl;
@@ -544,6 +562,11 @@ bool tagan_gemm_tma_supported(int64_t M, int64_t N, int64_t K, const float* A, i
 static inline int64_t presplit_ld(int64_t cols) { return (cols + 3) / 4 * 4; }
 static inline bool want_presplit(int32_t op, int64_t N, int64_t K) { return op != 2 && N * K <= PRESPLIT_MAX_ELEMS; }
 
+size_t tagan_gemm_tma_colsum_bytes(int64_t M, int64_t N, int64_t K) {
+  Plan pl = make_plan(M, N, K);
+  return 256 + 2 * (size_t)pl.splits * (size_t)M * sizeof(float);
+}
+
 size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K) {
   Plan pl = make_plan(M, N, K);
   size_t b = pl.splits > 1 ? (size_t)pl.splits * (size_t)M * (size_t)N * sizeof(float) : 0;
@@ -556,7 +579,7 @@ size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t 
 
 int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                    int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                   void* workspace, size_t workspace_bytes, cudaStream_t st, float* colsum_a /* TN only, [M] or null */) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
@@ -576,6 +599,13 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   if (pl.splits > 1) {
     if (!workspace || workspace_bytes < (size_t)pl.splits * M * N * sizeof(float)) return TAGAN_E_WORKSPACE;
     p.partial = static_cast<float*>(workspace);
+  }
+  p.colsum_part = nullptr;
+  if (colsum_a != nullptr) {
+    if (op != 2) return TAGAN_E_INVALID;
+    const size_t off = pl.splits > 1 ? ((size_t)pl.splits * M * N * sizeof(float) + 255) / 256 * 256 : 0;
+    if (!workspace || workspace_bytes < off + 2 * (size_t)pl.splits * M * sizeof(float)) return TAGAN_E_WORKSPACE;
+    p.colsum_part = reinterpret_cast<float*>(static_cast<char*>(workspace) + off);
   }
   if (p.partial) p.c_vec = (N % 4 == 0);
   else p.c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
@@ -605,5 +635,7 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   gemm_tma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2);
   if (p.partial)
     tma_splitk_reduce<<<ceil_div_i64(M * N, 256), 256, 0, st>>>(p.partial, pl.splits, M, N, bias, C, ldc, accumulate);
+  if (p.colsum_part)
+    colsum_parts_reduce<<<ceil_div_i64(M, 256), 256, 0, st>>>(p.colsum_part, 2 * pl.splits, M, colsum_a);
   return tagan_launch_status();
 }

@@ -222,6 +222,39 @@ __global__ void window_bwd_kernel(const float* __restrict__ dg, const float* __r
   }
 }
 
+// mean / sum aggregation, float4 columns: a thread walks u keeping the 2W+1 scaled gradients of its window in
+// registers, so every dg element is loaded once (the scalar kernel re-reads each 2W+1 times through L2).  The sum
+// runs over ascending t from 0.f exactly like the scalar kernel (out-of-range slots hold 0.f), so results are
+// bit-identical.
+template <int W>
+__global__ void window_bwd_vec_kernel(const float* __restrict__ dg, float* __restrict__ dp, int T, int64_t inner4, int agg) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= inner4) return;
+  const float4* g4 = reinterpret_cast<const float4*>(dg);
+  float4* o4 = reinterpret_cast<float4*>(dp);
+  auto fetch = [&](int t) -> float4 {
+    if (t < 0 || t >= T) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = g4[(int64_t)t * inner4 + x];
+    if (agg == 0) {
+      const float c = (float)(min(T, t + W + 1) - max(0, t - W));
+      v.x = v.x / c; v.y = v.y / c; v.z = v.z / c; v.w = v.w / c;
+    }
+    return v;
+  };
+  float4 win[2 * W + 1];
+#pragma unroll
+  for (int k = 0; k <= 2 * W; ++k) win[k] = fetch(k - W);
+  for (int u = 0; u < T; ++u) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k <= 2 * W; ++k) { s.x += win[k].x; s.y += win[k].y; s.z += win[k].z; s.w += win[k].w; }
+    o4[(int64_t)u * inner4 + x] = s;
+#pragma unroll
+    for (int k = 0; k < 2 * W; ++k) win[k] = win[k + 1];
+    win[2 * W] = fetch(u + 1 + W);
+  }
+}
+
 }  // namespace
 
 TAGAN_API int tagan_gates_fwd(const float* g, int64_t ldg, const float* second, int64_t lds, float* r, float* z,
@@ -293,6 +326,17 @@ TAGAN_API int tagan_skip_window_bwd(const float* dg, const float* p, const float
   if (!dg || !dp || T < 0 || inner < 0 || window < 0 || agg < 0 || agg > 2) return TAGAN_E_INVALID;
   if (agg == 1 && (!p || !agg_out)) return TAGAN_E_INVALID;
   if (T == 0 || inner == 0) return 0;
+  if (agg != 1 && inner % 4 == 0 && al16(dg) && al16(dp) && window >= 1 && window <= 4) {
+    const unsigned grid = ceil_div_i64(inner / 4, 256);
+    cudaStream_t st = as_stream(stream);
+    switch (window) {
+      case 1: window_bwd_vec_kernel<1><<<grid, 256, 0, st>>>(dg, dp, T, inner / 4, agg); break;
+      case 2: window_bwd_vec_kernel<2><<<grid, 256, 0, st>>>(dg, dp, T, inner / 4, agg); break;
+      case 3: window_bwd_vec_kernel<3><<<grid, 256, 0, st>>>(dg, dp, T, inner / 4, agg); break;
+      default: window_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(dg, dp, T, inner / 4, agg); break;
+    }
+    return tagan_launch_status();
+  }
   window_bwd_kernel<<<ceil_div_i64(inner, 256), 256, 0, as_stream(stream)>>>(dg, p, agg_out, dp, T, inner, window, agg);
   return tagan_launch_status();
 }

@@ -16,7 +16,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .ops import CALLS, _ptr, _stream, colsum, gemm, workspace
+from .ops import CALLS, _ptr, _stream, colsum, gemm, gemm_tn_colsum, workspace
 
 
 def _off(t: torch.Tensor, elems: int):
@@ -156,12 +156,11 @@ class _GRUScanFn(torch.autograd.Function):
         dxhat = torch.empty(rows, din, **f32)
         gemm(1, rows, din, 3 * hd, dg, 3 * hd, w_x, din, None, dxhat, din)
         dw_x = torch.empty(3 * hd, din, **f32)
-        gemm(2, 3 * hd, din, rows, dg, 3 * hd, xhat, din, None, dw_x, din)
+        db = gemm_tn_colsum(3 * hd, din, rows, dg, 3 * hd, xhat, din, dw_x, din)     # dW_x and the bias gradients
         dw_h_rz = torch.empty(2 * hd, hd, **f32)
         gemm(2, 2 * hd, hd, rows, dg, 3 * hd, hhat, hd, None, dw_h_rz, hd)
         dw_h_c = torch.empty(hd, hd, **f32)
         gemm(2, hd, hd, rows, _off(dg, 2 * hd), 3 * hd, rs, hd, None, dw_h_c, hd)
-        db = colsum(dg, rows, 3 * hd, 3 * hd)
         dlnx_w = dlnx_b = None
         if use_ln:
             dx = torch.empty(rows, din, **f32)

@@ -215,6 +215,21 @@ def colsum(x2d: torch.Tensor, rows: int, cols: int, ld: int) -> torch.Tensor:
     return out
 
 
+def gemm_tn_colsum(m: int, n: int, k: int, a, lda, b, ldb, c, ldc) -> torch.Tensor:
+    """C[m,n] = A[k,m]^T . B[k,n] and returns colsum(A) [m]  (dW and db of a Linear in one pass over dY)."""
+    lib = _lib.load()
+    dev = c.device
+    out = torch.empty(m, dtype=torch.float32, device=dev)
+    nbytes = lib.tagan_gemm_tn_colsum_workspace_bytes(m, n, k)
+    ws = workspace(nbytes, dev)
+    with _timed("gemm"):
+        rc = lib.tagan_gemm_tn_colsum(m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(c), ldc, _ptr(out), GEMM_PRECISION,
+                                      _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "tagan_gemm_tn_colsum")
+    CALLS["n"] += 3
+    return out
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b  (nn.Linear); dX = dY W, dW = dY^T X, db = colsum(dY)."""
 
@@ -240,11 +255,15 @@ class _LinearFn(torch.autograd.Function):
             dx = torch.empty(m, k, dtype=torch.float32, device=dy.device)
             gemm(1, m, k, n, dy2, ldy, w, w.stride(0), None, dx, k)
             dx = dx.view(ctx.in_shape)
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             dw = torch.empty(n, k, dtype=torch.float32, device=dy.device)
             ldx = x2.stride(0) if m > 1 else k
-            gemm(2, n, k, m, dy2, ldy, x2, ldx, None, dw, k)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if want_db:
+                db = gemm_tn_colsum(n, k, m, dy2, ldy, x2, ldx, dw, k)
+            else:
+                gemm(2, n, k, m, dy2, ldy, x2, ldx, None, dw, k)
+        elif want_db:
             db = colsum(dy2, m, n, ldy)
         return dx, dw, db
 

@@ -111,3 +111,25 @@ def test_linear_autograd_with_tensor_core_gemm():
         torch.testing.assert_close(wd.grad.cpu(), wt.grad, rtol=1e-4, atol=2e-5)
     finally:
         ops.GEMM_PRECISION = old
+
+
+@pytest.mark.parametrize("m,n,k", [(384, 128, 100_000), (128, 128, 3000), (200, 72, 1031), (512, 256, 40_000), (16, 16, 50)])
+def test_gemm_tn_colsum(m, n, k):
+    """dW = A^T B with the column sums of A (the bias gradient) accumulated in the same pass: both outputs against
+    fp64 torch (dW to the 3xTF32 tolerance of the other GEMM tests, column sums to fp32 summation-order tolerance),
+    and bit-identical reruns (fixed-order partial reductions)."""
+    from tagan_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(m + n + k)
+    a = torch.randn(k, m, device=dev)
+    b = torch.randn(k, n, device=dev)
+    c = torch.empty(m, n, device=dev)
+    cs = ops.gemm_tn_colsum(m, n, k, a, m, b, n, c, n)
+    ref = (a.double().t() @ b.double())
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(c.double(), ref, rtol=1e-4, atol=1e-5 * max(1.0, scale))      # the file's parity bar
+    cref = a.double().sum(0)
+    assert float((cs.double() - cref).abs().max()) <= 1e-5 * max(1.0, float(cref.abs().max()))
+    c2 = torch.empty_like(c)
+    cs2 = ops.gemm_tn_colsum(m, n, k, a, m, b, n, c2, n)
+    assert torch.equal(c, c2) and torch.equal(cs, cs2)
