@@ -381,8 +381,11 @@ TAGAN_API int tagan_tattn_fwd(const float* Q, const float* K, const float* V, in
     default: rc = set_smem(tattn_fwd_kernel<64>, c.smem); break;
   }
   if (rc) return rc;
-  const bool fast = T <= 32 && c.warps * c.PPW >= heads && bias_bstride == 0 && c.smem <= 48 * 1024 &&
-                    (bias == nullptr) == (bias_t == nullptr);
+  const bool shared_bias = bias_bstride == 0 && (bias == nullptr) == (bias_t == nullptr);
+  if (shared_bias && tagan_tattn_fwd_mma_launch(D, (int)(B < 148 * 4 ? B : 148 * 4), st, Q, K, V, ld, B, T, heads, rsb, rst,
+                                                bias, ms, ctx, lse, attn))
+    return tagan_launch_status();
+  const bool fast = T <= 32 && c.warps * c.PPW >= heads && shared_bias && c.smem <= 48 * 1024;
   if (fast && tagan_tattn_fwd_fast_launch(D, c.TP, grid, c.warps * 32, c.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
                                           ctx, lse, attn))
     return tagan_launch_status();

@@ -64,3 +64,8 @@ bool tagan_tattn_bwd_fast_launch(int D, int TP, int grid, int threads, size_t sm
                                  const float* K, const float* V, int64_t ld, int64_t B, int T, int heads, int64_t rsb,
                                  int64_t rst, const float* bias, MaskSpec ms, const float* ctx, const float* lse,
                                  const float* dctx, float* dQ, float* dK, float* dV, int64_t ldd, float* dbias_partial);
+
+// tensor-core kernels for 8 < T <= 16 (temporal_attn_fast.cu); return false when the shape is not covered
+bool tagan_tattn_fwd_mma_launch(int D, int grid, cudaStream_t st, const float* Q, const float* K, const float* V, int64_t ld,
+                                int64_t B, int T, int heads, int64_t rsb, int64_t rst, const float* bias, MaskSpec ms,
+                                float* ctx, float* lse, float* attn);

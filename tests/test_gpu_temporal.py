@@ -75,7 +75,7 @@ def test_temporal_attention_vs_reference_golden(dev, golden):
 
 
 @pytest.mark.parametrize("b,t,hidden,heads", [(33, 16, 128, 8), (7, 32, 128, 4), (5, 48, 64, 4), (3, 128, 128, 8),
-                                              (9, 5, 64, 4), (4, 16, 256, 8), (6, 11, 40, 5)])
+                                              (9, 5, 64, 4), (4, 16, 256, 8), (6, 11, 40, 5), (6, 11, 64, 4), (5, 9, 256, 8)])
 @pytest.mark.parametrize("mode", ["shared_ts", "no_ts_causal", "per_node_ts", "mask3d"])
 def test_temporal_attention_vs_oracle_shapes(dev, b, t, hidden, heads, mode):
     import tagan_b200
