@@ -307,6 +307,25 @@ colsum_vec_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ 
   }
 }
 
+// the two affine gradients of a LayerNorm in one launch: partial rows are [dgamma cols | dbeta cols]
+__global__ void __launch_bounds__(256)
+reduce_parts2_kernel(const float* __restrict__ partial, int parts, int64_t stride, int cols, float* __restrict__ out_a,
+                     float* __restrict__ out_b) {
+  __shared__ float red[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < 2 * cols)
+    for (int p = slice; p < parts; p += 8) s += partial[(int64_t)p * stride + c];
+  red[slice][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (slice == 0 && c < 2 * cols) {
+    float t = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][threadIdx.x];
+    if (c < cols) out_a[c] = t; else out_b[c - cols] = t;
+  }
+}
+
 // out[c] = sum over parts of partial[p][c] for `nvec` stacked vectors of `cols` (fixed order: 8 interleaved
 // slices, then the slices in order) -- 32 columns per block
 __global__ void __launch_bounds__(256)
@@ -442,8 +461,10 @@ TAGAN_API int tagan_layernorm_bwd(const float* dy, int64_t lddy, const float* xs
   }
   if (want_affine) {
     // partial layout [parts][2][cols]: dgamma rows at offset 0, dbeta rows at offset cols
-    if (dgamma) reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(part, parts, 2 * (int64_t)cols, cols, dgamma);
-    if (dbeta) reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(part + cols, parts, 2 * (int64_t)cols, cols, dbeta);
+    if (dgamma && dbeta)          // one launch over the 2*cols stacked columns, same summation order per column
+      reduce_parts2_kernel<<<(2 * cols + 31) / 32, 256, 0, st>>>(part, parts, 2 * (int64_t)cols, cols, dgamma, dbeta);
+    else if (dgamma) reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(part, parts, 2 * (int64_t)cols, cols, dgamma);
+    else if (dbeta) reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(part + cols, parts, 2 * (int64_t)cols, cols, dbeta);
   }
   return tagan_launch_status();
 }
