@@ -4,12 +4,15 @@
 //   C[M,N] = op(A) . op(B)   NT / NN / TN as in gemm_tc.cu, fp32-accurate through the TF32 hi/lo split.
 //
 // Warp roles of the persistent CTA (one per SM, 14 warps):
-//   warps 0-3   epilogue  : tcgen05.ld -> padded smem -> row-contiguous 128 B stores (+bias / +C)
-//   warp  4     MMA       : one thread issues tcgen05.mma.kind::tf32 (lo.hi, hi.lo, hi.hi per k-step); the A operand
-//                           is read from TENSOR MEMORY (lane = row), B through a shared-memory descriptor
+//   warps 0-3   epilogue  : tcgen05.ld -> padded smem -> row-contiguous 128 B stores (+bias / +C); straight-line code
+//                           for interior tiles
+//   warp  4     MMA       : warp-uniform loop, tcgen05.mma.kind::tf32 (lo.hi, hi.lo, hi.hi per k-step) issued under
+//                           elect.sync so descriptors / TMEM addresses stay in uniform registers; the A operand is
+//                           read from TENSOR MEMORY (lane = row), B through a shared-memory descriptor
 //   warp  5     TMA       : one thread issues cp.async.bulk.tensor loads of the raw fp32 A/B tiles straight
-//                           into their final 128B-swizzled positions (K-major: one 128x32 box with
-//                           SWIZZLE_128B; MN-major: four 32x32 boxes with SWIZZLE_128B_ATOM_32B), completing
+//                           into their final positions (B: 128B-swizzled UMMA tiles -- K-major one 128x32 box
+//                           with SWIZZLE_128B, MN-major four 32x32 boxes with SWIZZLE_128B_ATOM_32B; raw A: the same
+//                           K-major box, or four unswizzled 32x32 boxes when MN-major), completing
 //                           on an mbarrier with expect_tx; it runs up to STAGES k-blocks ahead, so the HBM
 //                           stream is never exposed to thread-level latency and costs no registers
 //   warps 6-13  split     : A: raw smem tile -> registers -> hi = rn_tf32(x), lo = rn_tf32(x - hi) -> tcgen05.st into the
