@@ -11,9 +11,9 @@ from .layers import (AsymmetricTemporalAttention, GeometricAttention, LayerNorm,
                      TemporalSkipConnection, TimeEncoding)
 
 from .memory_bank import NodeMemoryBank  # noqa: F401,E402
-from .model import TAGANLayer, patch  # noqa: F401,E402
+from .model import TAGANLayer, forward_node_partitioned, patch  # noqa: F401,E402
 from .graphed import GraphedStep  # noqa: F401,E402
 
-__all__ = ["NodeMemoryBank", "TAGANLayer", "patch", "GraphedStep", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
+__all__ = ["NodeMemoryBank", "TAGANLayer", "patch", "GraphedStep", "forward_node_partitioned", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
            "TemporalGRUCell", "TemporalEvolutionLayer", "TemporalSkipConnection", "TemporalGatingUnit",
            "TemporalPropagation"]

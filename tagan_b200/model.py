@@ -58,6 +58,30 @@ class TAGANLayer(nn.Module):
         return self.temporal_attention(prop, time_stamps=time_stamps, time_major=True)
 
 
+def forward_node_partitioned(layer: "TAGANLayer", xs_loc: Sequence[torch.Tensor], edge_indices: Sequence[torch.Tensor],
+                             part, rank: int, comm, time_stamps: Optional[torch.Tensor] = None,
+                             bank: Optional[NodeMemoryBank] = None) -> torch.Tensor:
+    """``TAGANLayer.forward`` for ONE large graph whose nodes are partitioned over the ranks (config 4).
+
+    ``xs_loc``: this rank's rows ``[n_loc,H]`` of every snapshot; ``edge_indices``: the GLOBAL edge lists (every
+    rank builds only its own rows of the CSR).  The geometric layer exchanges K|V halos (software-pipelined
+    all-gather / reduce-scatter, ``partitioned.geometric_stage_part``); everything after it -- GRU scan, skip
+    connection, temporal attention, memory bank -- is per node and therefore purely local.  Weights are replicated:
+    all-reduce their gradients after backward (``dist.GradBucket``).  Returns this rank's ``[n_loc,T,H]``."""
+    from . import partitioned
+    ga = layer.geometric.geometric_attention
+    csrs = [partitioned.build_csr_part(ei, part, rank) for ei in edge_indices]
+    geo = torch.stack(partitioned.geometric_stage_part(ga, list(xs_loc), csrs, comm, part.num_nodes), 0)
+    prop = layer.propagation.forward_core(geo, time_stamps)                          # [T,n_loc,H], local
+    if bank is not None:
+        n_loc = prop.shape[1]
+        ids = torch.arange(n_loc, dtype=torch.int32, device=prop.device)             # bank slots are local row ids
+        for t in range(prop.shape[0]):
+            bank.get_states(ids)
+            bank.update(ids, prop[t].detach(), t)
+    return layer.temporal_attention(prop, time_stamps=time_stamps, time_major=True)
+
+
 def patch(model: nn.Module) -> nn.Module:
     """Swap the hot-path layers of a reference ``TAGAN`` for the B200 ones, in place.
 
