@@ -50,3 +50,27 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "ref_loader" not in src and "/root/reference" not in src, f
+
+
+def test_stack_rows_is_a_view_of_sliced_buffers():
+    """ops.stack_rows (host logic): consecutive slices of one allocation stack for free; anything else falls back to
+    torch.stack with identical values."""
+    import torch
+    from tagan_b200 import ops
+    buf = torch.arange(4 * 3 * 5, dtype=torch.float32).reshape(4, 3, 5)
+    xs = list(buf.unbind(0))
+    out = ops.stack_rows(xs)
+    assert out.data_ptr() == buf.data_ptr() and torch.equal(out, buf)
+    shuffled = [xs[1], xs[0], xs[2], xs[3]]                      # same storage, wrong order -> copy
+    out2 = ops.stack_rows(shuffled)
+    assert out2.data_ptr() != buf.data_ptr() and torch.equal(out2, torch.stack(shuffled, 0))
+    separate = [x.clone() for x in xs]
+    assert torch.equal(ops.stack_rows(separate), buf)
+    grads = [x.clone().requires_grad_(True) for x in xs]         # gradient-carrying inputs keep autograd's stack
+    assert ops.stack_rows(grads).grad_fn is not None
+
+
+def test_workspace_query_of_fused_linear_backward():
+    from tagan_b200 import _lib
+    lib = _lib.load()
+    assert lib.tagan_gemm_tn_colsum_workspace_bytes(384, 128, 1_600_000) >= lib.tagan_gemm_workspace_bytes(2, 384, 128, 1_600_000)
