@@ -142,11 +142,14 @@ template <typename F>
 __device__ __forceinline__ void for_each_heavy_row(const int* __restrict__ ptr, int N, F f) {
   __shared__ int heavy_list[WARPS_PER_BLOCK * 32];
   __shared__ int heavy_count;
-  for (int base = blockIdx.x * (WARPS_PER_BLOCK * 32); base < N; base += gridDim.x * (WARPS_PER_BLOCK * 32)) {
+  // Rows are dealt to the CTAs round-robin (thread t of CTA b looks at row chunk + t*gridDim + b): hubs of generated and
+  // real power-law graphs have neighbouring (small) ids, and a contiguous block of rows per CTA would serialise all of
+  // them on one CTA.
+  for (int64_t chunk = 0; chunk < N; chunk += (int64_t)gridDim.x * (WARPS_PER_BLOCK * 32)) {
     if (threadIdx.x == 0) heavy_count = 0;
     __syncthreads();
-    const int r = base + threadIdx.x;
-    if (r < N && ptr[r + 1] - ptr[r] > HEAVY_THRESH) heavy_list[atomicAdd(&heavy_count, 1)] = r;
+    const int64_t r = chunk + (int64_t)threadIdx.x * gridDim.x + blockIdx.x;
+    if (r < N && ptr[r + 1] - ptr[r] > HEAVY_THRESH) heavy_list[atomicAdd(&heavy_count, 1)] = (int)r;
     __syncthreads();
     const int cnt = heavy_count;
     for (int i = 0; i < cnt; ++i) {
