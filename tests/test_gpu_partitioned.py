@@ -150,3 +150,29 @@ def test_pipelined_stage_matches_per_snapshot_layer():
         torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-6)
     for k, p in layer.named_parameters():
         torch.testing.assert_close(p.grad, gref[k], rtol=1e-5, atol=1e-5 * max(1.0, float(gref[k].abs().max())))
+
+
+def test_forward_node_partitioned_world1_matches_layer():
+    """forward_node_partitioned (whole TAGAN layer on a node-partitioned graph) with a single rank == TAGANLayer.forward:
+    same CSR rows, same kernels, identity collectives -> bit-identical forward, gradients to summation order."""
+    import tagan_b200
+    from tagan_b200.dist import NodePartition
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    n, e, hdim, heads, t_steps = 640, 5000, 64, 4, 5
+    layer = tagan_b200.TAGANLayer(hdim, heads, "euclidean").to(dev)
+    xs = [torch.randn(n, hdim, device=dev) for _ in range(t_steps)]
+    eis = [torch.randint(0, n, (2, e), device=dev) for _ in range(t_steps)]
+    ts = torch.arange(t_steps, dtype=torch.float32, device=dev).expand(n, t_steps)
+    wout = torch.randn(n, t_steps, hdim, device=dev)
+    ref = layer(xs, eis, ts)
+    (ref * wout).sum().backward()
+    gref = {k: p.grad.clone() for k, p in layer.named_parameters() if p.grad is not None}
+    layer.zero_grad(set_to_none=True)
+    out = tagan_b200.forward_node_partitioned(layer, xs, eis, NodePartition(n, 1), 0, OneRankComm(), ts)
+    (out * wout).sum().backward()
+    assert torch.equal(out, ref)
+    for k, p in layer.named_parameters():
+        if k in gref:
+            torch.testing.assert_close(p.grad, gref[k], rtol=1e-4, atol=1e-4 * max(1.0, float(gref[k].abs().max())),
+                                       msg=lambda m, k=k: f"{k}: {m}")
