@@ -440,7 +440,7 @@ TAGAN_API int tagan_tattn_bwd(const float* Q, const float* K, const float* V, in
   if (rc) return rc;
   Cfg cf;                                                // the fast kernel parks P and dS in smem: larger slots
   const bool fast = T <= 32 && !per_node && make_cfg(T, D, heads, tattn_bwd_fast_slot_floats(T, D, c.TP), &cf) &&
-                    cf.warps * cf.PPW >= heads && cf.smem <= 72 * 1024;
+                    cf.warps * cf.PPW >= heads && cf.smem <= 100 * 1024;
   if (fast && tagan_tattn_bwd_fast_launch(D, cf.TP, grid, cf.warps * 32, cf.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
                                           ctx, lse, dctx, dQ, dK, dV, ldd, db_target)) {
   } else {

@@ -431,8 +431,7 @@ tattn_fwd_mma_kernel(const float* __restrict__ Q, const float* __restrict__ K, c
   }
 }
 
-// instantiated (D, TP) pairs: head dims 8/16/32 x padded lengths 8/16/32 (except 32x32, whose unrolled body is
-// too large to pay off); everything else takes the generic kernels
+// instantiated (D, TP) pairs: head dims 8/16/32 x padded lengths 8/16/32; everything else takes the generic kernels
 template <int D, int TP>
 void tattn_bwd_fast_launch_one(int grid, int threads, size_t smem, cudaStream_t st, const float* Q, const float* K,
                                const float* V, int64_t ld, int64_t B, int T, int heads, int64_t rsb, int64_t rst,
@@ -457,6 +456,7 @@ void tattn_bwd_fast_launch_one(int grid, int threads, size_t smem, cudaStream_t 
     case 16 * 64 + 32: FN<16, 32> __VA_ARGS__; return true;           \
     case 32 * 64 + 8: FN<32, 8> __VA_ARGS__; return true;             \
     case 32 * 64 + 16: FN<32, 16> __VA_ARGS__; return true;           \
+    case 32 * 64 + 32: FN<32, 32> __VA_ARGS__; return true;           \
     default: return false;                                     \
   }
 
