@@ -173,7 +173,7 @@ def peaks():
 def run_ours(args):
     import torch.distributed as dist
     import tagan_b200
-    from tagan_b200 import ops, synth
+    from tagan_b200 import fused, ops, synth
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the TAGAN hot path has no CPU fallback "
                          "(use --impl reference for the CPU oracle arm)")
@@ -207,7 +207,7 @@ def run_ours(args):
         out = layer(xs, eis, ts_d, bank=bank, node_ids=[ids] * t_steps)       # [N,T,H] view of time-major storage
         # mean of squares, taken in the storage order of `out` (a permutation of the same elements) so that the
         # loss and its gradient are contiguous element-wise passes instead of strided ones
-        loss = out.permute(1, 0, 2).square().mean()
+        loss = fused.mean_square(out.permute(1, 0, 2))
         loss.backward()
         return loss
 
@@ -300,7 +300,8 @@ def run_ours(args):
     value = units_per_step / (ms_step * 1e-3)
 
     # ---- live per-kernel timing and roofline of the dominant kernel ---------------------------
-    kt = {k: [s.elapsed_time(t) for s, t in v] for k, v in prof.items()}
+    kt = {k: [s.elapsed_time(t) for s, t, _ in v] for k, v in prof.items()}
+    kbytes = {k: sum(b for _, _, b in v) for k, v in prof.items()}
     share = {k: sum(v) / (ms_step * args.steps) for k, v in kt.items()}
     h = w.heads
     mean_nnz = sum(nnz) / len(nnz)
@@ -323,9 +324,28 @@ def run_ours(args):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(args.workload, {}).get("geo_attn_bwd")
+            tr = json.load(open(traffic_file)).get(args.workload, {})
+            roofline["traffic"] = tr.get("geo_attn_bwd")
+            roofline["traffic_source"] = tr.get("source", "profiles/traffic.json (ncu --set full, dram__bytes_read+write per launch)")
         except Exception:
             pass
+    # all projections (tcgen05 GEMMs, fused epilogues included): algorithmic bytes of every call / summed event time
+    if kt.get("gemm"):
+        g_ms = sum(kt["gemm"]) / args.steps
+        g_gb = kbytes["gemm"] / args.steps / 1e9
+        roofline["gemm"] = {"bound": "hbm (K <= 256 projections stream their operands)", "calls_per_step": len(kt["gemm"]) // args.steps,
+                            "algorithmic_gb_per_step": g_gb, "ms_per_step": g_ms, "achieved": g_gb / (g_ms * 1e-3),
+                            "frac": g_gb / (g_ms * 1e-3) / peak, "unit": "GB/s"}
+    # whole layer against the SURVEY section 8d byte budget: kernel (a) + node stream (73*H*4 B per node-snapshot)
+    # + kernel (b) core (11*T*H*4 B per node) + memory bank (gather, update, sweep), per step
+    s4 = 4
+    wl_bytes = (t_steps * (bytes_fwd + bytes_bwd) + 73 * hdim * s4 * n * t_steps + 11 * t_steps * hdim * s4 * n)
+    if not args.no_bank:
+        wl_bytes += t_steps * n * ((2 * hdim * s4 + 4) + (3 * hdim * s4 + 16) + (2 * hdim * s4 + 8))
+    roofline["whole_layer"] = {"algorithmic_gb_per_step": wl_bytes / 1e9, "ms_per_step": ms_step,
+                               "achieved": wl_bytes / 1e9 / (ms_step * 1e-3), "frac": wl_bytes / 1e9 / (ms_step * 1e-3) / peak,
+                               "unit": "GB/s", "budget": "SURVEY.md section 8d: kernel (a) fwd+bwd + 73*H*4 B node stream per "
+                               "node-snapshot + 11*T*H*4 B kernel (b) per node + bank"}
 
     # ---- e2e arm: host buffers, H2D copies and D2H loss read inside the timed region ----------
     e2e = None
@@ -404,11 +424,15 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cstep, cunits, cdesc = cpu_sample_step_factory(w, args.metric)
-        t0 = time.perf_counter()
-        cstep()
-        cdt = time.perf_counter() - t0
+        cstep()                                                  # warm-up (page faults, thread pool)
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            cstep()
+            times.append(time.perf_counter() - t0)
+        cdt = statistics.median(times)
         cpu = {"value": cunits / cdt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": cdesc,
-               "seconds": cdt}
+               "seconds": cdt, "protocol": "1 warm-up + median of 3"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -418,7 +442,11 @@ def run_ours(args):
                            "hidden": hdim, "heads": h, "distance_metric": args.metric,
                            "parallelism": f"dp{world} (one sequence per GPU, NCCL grad all-reduce)",
                            "memory_bank": not args.no_bank,
-                           "l2": "inputs larger than L2 (each step streams > 10 GB)"},
+                           "l2": ("inputs larger than L2: one step streams %.0f GB of activations through a 126 MB L2 "
+                                  "(per-snapshot K/V of %.0f MB %s)" % (
+                                      wl_bytes / 1e9, n * hdim * 4 / 1e6,
+                                      "fit L2, so kernel (a)'s gathers are L2 hits" if n * hdim * 8 < 100e6
+                                      else "do not fit L2"))},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "timing": {"mode": timing_mode, "eager_ms_per_step": eager_ms_step}}
         print(json.dumps(line), flush=True)

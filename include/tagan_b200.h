@@ -175,6 +175,100 @@ int tagan_gemm_tn_colsum(int64_t m, int64_t n, int64_t k, const float* A, int64_
                          void* workspace, size_t workspace_bytes, tagan_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Projections with the reference's surrounding element-wise / LayerNorm code fused into the GEMM
+ * (SURVEY.md section 8b "tagan_gemm_ln_qkv / tagan_gemm_out_res_ln / tagan_gru_epilogue_*"): the
+ * accumulator tile is consumed in registers, the intermediate never makes an HBM round trip.
+ *
+ *   acc[M,N] = [A | A2][M, K] . op(B) (+ bias[N])            op 0 = NT (B[N,K]), 1 = NN (B[K,N])
+ *   A2 != NULL: the A operand is the column concatenation of A[M,k1] and A2[M,K-k1] (k1 % 32 == 0, NT only) --
+ *   the reference's `torch.cat([x, h], dim=-1)` feeding reset/update/candidate Linears
+ *   (src/tagan/layers/temporal_propagation.py:531-538) without materialising the concatenation.
+ *
+ *   TAGAN_EPI_STORE      out0 = acc
+ *   TAGAN_EPI_RES_LN     v = acc + in0 (in0 NULL: none); out1 = v if out1 != NULL (saved for backward);
+ *                        out0 = LayerNorm(v; gamma, beta, eps 1e-5), mean/rstd [M] optional; gamma NULL: out0 = v.
+ *                        `output_proj -> dropout(p=0) -> + identity -> layer_norm2`
+ *                        (geometric_attention.py:586-596, temporal_attention.py:1186-1200,
+ *                        temporal_propagation.py:738-753, :929-944, :1487-1500).  Needs N <= 128.
+ *   TAGAN_EPI_GATES      s = sigmoid(acc); columns < split: out0 = s (reset gate r), out1 = s * in0 (r * h^);
+ *                        columns >= split: out2[:, col-split] = s (update gate z)   (temporal_propagation.py:531-535)
+ *   TAGAN_EPI_BLEND      t = tanh(acc); out0 = t (candidate); out1 = (1-in0)*in1 + in0*t, in0 = z, in1 = h^  (:538-542)
+ *   TAGAN_EPI_GATES_BWD  d = acc (= d(r*h^)); out0 = d * in1 * r(1-r) with r = in0, h^ = in1; out1 += d * r
+ *                        (autograd of :531-538; out0 is the gradient of the reset pre-activation)
+ * All pointers 16-byte aligned, every leading dimension and N a multiple of 4.  Returns TAGAN_E_UNSUPPORTED when
+ * the shape cannot take the fused path (the caller then composes tagan_gemm with the stand-alone kernels).
+ * ------------------------------------------------------------------------------------- */
+enum tagan_epi_mode {
+  TAGAN_EPI_STORE = 0,
+  TAGAN_EPI_RES_LN = 1,
+  TAGAN_EPI_GATES = 2,
+  TAGAN_EPI_BLEND = 3,
+  TAGAN_EPI_GATES_BWD = 4
+};
+struct tagan_epilogue {
+  int32_t mode;
+  int32_t split;
+  const float* in0; int64_t ld_in0;
+  const float* in1; int64_t ld_in1;
+  float* out0; int64_t ld_out0;
+  float* out1; int64_t ld_out1;
+  float* out2; int64_t ld_out2;
+  const float* gamma;
+  const float* beta;
+  float* mean;
+  float* rstd;
+};
+size_t tagan_gemm_fused_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k);
+int tagan_gemm_fused(int32_t op /*0=NT,1=NN*/, int64_t m, int64_t n, int64_t k,
+                     const float* A, int64_t lda, const float* A2, int64_t lda2, int64_t k1,
+                     const float* B, int64_t ldb, const float* bias, const struct tagan_epilogue* epi,
+                     int32_t precision, void* workspace, size_t workspace_bytes, tagan_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused node-stream passes of the propagation core (csrc/fused_rows.cu): one pass over the rows instead of a chain
+ * of element-wise / LayerNorm launches.  cols <= 512; affine gradients are deterministic (fixed-order partials).
+ *
+ * tagan_ln_pair_fwd: s = LN_out(hn) and, if hhat != NULL, hhat = LN_h(s) * exp(-clamp(ts[:,t_hi]-ts[:,t_hi-1],0,10))
+ *   -- the state of the GRU scan between two steps (TemporalGRUCell.forward, temporal_propagation.py:545-546 then
+ *   :505-514 of the next step).  ts NULL: no decay.  decay[rows] (optional) receives the row scale for backward.
+ * tagan_ln_pair_bwd: dhn = dLN_out(ds_ext + dLN_h(dhh * decay)); daffine[4][cols] (+)= d gamma_o, d beta_o,
+ *   d gamma_h, d beta_h.  ds_ext / dhh may be NULL (no external gradient / last step).
+ * tagan_gelu_ln_fwd/bwd: y = LN(GELU(a)) (TemporalSkipConnection.forward :866-877); daffine[2][cols] = d gamma, d beta.
+ * tagan_window_gelu_fwd/bwd: out[t] = GELU(agg_{|u-t|<=window} p[u]) over the leading axis of p [T, inner], agg 0 = mean,
+ *   2 = sum (:880-894 followed by the activation of :929-933); backward rebuilds the aggregate from p.
+ * tagan_mse_fwd/bwd: *loss = mean(x^2); dx = (*dloss) * 2 x / n (dloss NULL = 1).
+ * ------------------------------------------------------------------------------------- */
+int tagan_ln_pair_fwd(const float* hn, int64_t ldhn, const float* gamma_o, const float* beta_o,
+                      const float* gamma_h, const float* beta_h, const float* ts, int64_t ldts, int32_t t_hi,
+                      float* s, int64_t lds, float* hhat, int64_t ldhh, float* mean_o, float* rstd_o,
+                      float* mean_h, float* rstd_h, float* decay, int64_t rows, int32_t cols, tagan_stream_t stream);
+size_t tagan_ln_pair_bwd_workspace_bytes(int64_t rows, int32_t cols);
+int tagan_ln_pair_bwd(const float* ds_ext, int64_t ldds, const float* dhh, int64_t lddhh, const float* hn, int64_t ldhn,
+                      const float* gamma_o, const float* beta_o, const float* gamma_h,
+                      const float* mean_o, const float* rstd_o, const float* mean_h, const float* rstd_h,
+                      const float* decay, float* dhn, int64_t lddhn, float* daffine, int32_t accumulate,
+                      void* workspace, size_t workspace_bytes, int64_t rows, int32_t cols, tagan_stream_t stream);
+int tagan_gelu_ln_fwd(const float* a, int64_t lda, const float* gamma, const float* beta, float* y, int64_t ldy,
+                      float* mean, float* rstd, int64_t rows, int32_t cols, tagan_stream_t stream);
+size_t tagan_gelu_ln_bwd_workspace_bytes(int64_t rows, int32_t cols);
+int tagan_gelu_ln_bwd(const float* dy, int64_t lddy, const float* a, int64_t lda, const float* gamma,
+                      const float* mean, const float* rstd, float* da, int64_t ldda, float* daffine,
+                      void* workspace, size_t workspace_bytes, int64_t rows, int32_t cols, tagan_stream_t stream);
+int tagan_window_gelu_fwd(const float* p, float* out, int32_t T, int64_t inner, int32_t window, int32_t agg,
+                          tagan_stream_t stream);
+int tagan_window_gelu_bwd(const float* dgg, const float* p, float* dp, int32_t T, int64_t inner, int32_t window,
+                          int32_t agg, tagan_stream_t stream);
+/* GRU blend backward (autograd of temporal_propagation.py:538-542) writing the gate pre-activation gradients into
+ * their column slices of the step's [rows,3H] gradient tile: dgz = dhn*(cand-hhat)*z(1-z), dgc = dhn*z*(1-cand^2),
+ * dhh = dhn*(1-z). */
+int tagan_gru_blend_bwd(const float* dhn, const float* z, const float* cand, const float* hhat, int64_t ldhh,
+                        float* dgz, float* dgc, int64_t lddg, float* dhh, int64_t lddhh, int64_t rows, int32_t H,
+                        tagan_stream_t stream);
+size_t tagan_mse_workspace_bytes(void);
+int tagan_mse_fwd(const float* x, int64_t n, float* loss, void* workspace, size_t workspace_bytes, tagan_stream_t stream);
+int tagan_mse_bwd(const float* x, int64_t n, const float* dloss, float* dx, tagan_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * (b1,b2) per-node temporal attention over the snapshot axis.
  * Replaces the score/bias/mask/softmax/`attn @ v` core of AsymmetricTemporalAttention.forward
  * (src/tagan/layers/temporal_attention.py:1008-1183).  One CTA per node, (node,head) pairs on

@@ -17,6 +17,16 @@ _f32 = C.c_float
 _sz = C.c_size_t
 
 
+class Epilogue(C.Structure):
+    """struct tagan_epilogue (fused GEMM epilogues, include/tagan_b200.h)"""
+    _fields_ = [("mode", _i32), ("split", _i32), ("in0", _p), ("ld_in0", _i64), ("in1", _p), ("ld_in1", _i64),
+                ("out0", _p), ("ld_out0", _i64), ("out1", _p), ("ld_out1", _i64), ("out2", _p), ("ld_out2", _i64),
+                ("gamma", _p), ("beta", _p), ("mean", _p), ("rstd", _p)]
+
+
+EPI_STORE, EPI_RES_LN, EPI_GATES, EPI_BLEND, EPI_GATES_BWD = range(5)
+
+
 class TimeParams(C.Structure):
     """struct tagan_time_params"""
     _fields_ = [("range", _p), ("mu", _p), ("inv2sig2", _p), ("wc", _p), ("bc", _p), ("nb", _i32)]
@@ -44,6 +54,23 @@ SIGNATURES = {
     "tagan_gemm": (_i32, [_i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _sz, _p]),
     "tagan_gemm_tn_colsum_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "tagan_gemm_tn_colsum": (_i32, [_i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _sz, _p]),
+    "tagan_gemm_fused_workspace_bytes": (_sz, [_i32, _i64, _i64, _i64]),
+    "tagan_gemm_fused": (_i32, [_i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p, C.POINTER(Epilogue), _i32,
+                                _p, _sz, _p]),
+    "tagan_ln_pair_fwd": (_i32, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64,
+                                 _i32, _p]),
+    "tagan_ln_pair_bwd_workspace_bytes": (_sz, [_i64, _i32]),
+    "tagan_ln_pair_bwd": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i32, _p, _sz,
+                                 _i64, _i32, _p]),
+    "tagan_gelu_ln_fwd": (_i32, [_p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i32, _p]),
+    "tagan_gelu_ln_bwd_workspace_bytes": (_sz, [_i64, _i32]),
+    "tagan_gelu_ln_bwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _sz, _i64, _i32, _p]),
+    "tagan_window_gelu_fwd": (_i32, [_p, _p, _i32, _i64, _i32, _i32, _p]),
+    "tagan_window_gelu_bwd": (_i32, [_p, _p, _p, _i32, _i64, _i32, _i32, _p]),
+    "tagan_gru_blend_bwd": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
+    "tagan_mse_workspace_bytes": (_sz, []),
+    "tagan_mse_fwd": (_i32, [_p, _i64, _p, _p, _sz, _p]),
+    "tagan_mse_bwd": (_i32, [_p, _i64, _p, _p, _p]),
     "tagan_tattn_fwd": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _i64, _p, _i32, _f32, _p,
                                _p, _i32, _i32, _p, _p, _p, _p]),
     "tagan_tattn_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),

@@ -17,7 +17,8 @@ size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t 
 size_t tagan_gemm_tma_colsum_bytes(int64_t M, int64_t N, int64_t K);
 int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                    int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st, float* colsum_a);
+                   void* workspace, size_t workspace_bytes, cudaStream_t st, float* colsum_a,
+                   const float* A2 = nullptr, int64_t lda2 = 0, int64_t K1 = 0, const tagan_epilogue* epi = nullptr);
 
 TAGAN_API size_t tagan_gemm_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k) {
   if (op < 0 || op > 2 || m < 0 || n < 0 || k < 0) return 0;
@@ -76,3 +77,48 @@ TAGAN_API int tagan_gemm_tn_colsum(int64_t m, int64_t n, int64_t k, const float*
 }
 
 TAGAN_API int tagan_abi_version(void) { return 1; }
+
+
+// ---- fused-epilogue projections (tensor-core path only; the caller composes the stand-alone kernels otherwise) ----
+TAGAN_API size_t tagan_gemm_fused_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k) {
+  if (op < 0 || op > 1 || m < 0 || n < 0 || k < 0) return 0;
+  return tagan_gemm_tma_workspace_bytes(op, m, n, k);
+}
+
+static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+TAGAN_API int tagan_gemm_fused(int32_t op, int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* A2,
+                               int64_t lda2, int64_t k1, const float* B, int64_t ldb, const float* bias,
+                               const struct tagan_epilogue* epi, int32_t precision, void* workspace, size_t workspace_bytes,
+                               tagan_stream_t stream) {
+  if (op < 0 || op > 1 || m < 0 || n <= 0 || k <= 0 || !A || !B || !epi || !epi->out0) return TAGAN_E_INVALID;
+  if (precision < 1 || precision > 3) return TAGAN_E_INVALID;
+  if (m == 0) return 0;
+  const tagan_epilogue& e = *epi;
+  if (e.mode < TAGAN_EPI_STORE || e.mode > TAGAN_EPI_GATES_BWD) return TAGAN_E_INVALID;
+  if (n % 4 || !al16p(bias) || !al16p(e.out0) || e.ld_out0 % 4) return TAGAN_E_UNSUPPORTED;
+  if ((e.in0 && (!al16p(e.in0) || e.ld_in0 % 4)) || (e.in1 && (!al16p(e.in1) || e.ld_in1 % 4)) ||
+      (e.out1 && (!al16p(e.out1) || e.ld_out1 % 4)) || (e.out2 && (!al16p(e.out2) || e.ld_out2 % 4)))
+    return TAGAN_E_UNSUPPORTED;
+  switch (e.mode) {
+    case TAGAN_EPI_RES_LN:
+      if (e.gamma && (!e.beta || !al16p(e.gamma) || !al16p(e.beta) || n > 128)) return e.beta ? TAGAN_E_UNSUPPORTED : TAGAN_E_INVALID;
+      break;
+    case TAGAN_EPI_GATES:
+      if (!e.in0 || !e.out1 || !e.out2) return TAGAN_E_INVALID;
+      if (e.split <= 0 || e.split >= n || e.split % 4) return TAGAN_E_UNSUPPORTED;
+      break;
+    case TAGAN_EPI_BLEND:
+      if (!e.in0 || !e.in1 || !e.out1) return TAGAN_E_INVALID;
+      break;
+    case TAGAN_EPI_GATES_BWD:
+      if (!e.in0 || !e.in1 || !e.out1) return TAGAN_E_INVALID;
+      break;
+    default: break;
+  }
+  if (!tagan_gemm_tma_supported(m, n, k, A, lda, B, ldb)) return TAGAN_E_UNSUPPORTED;
+  if (A2 && ((reinterpret_cast<uintptr_t>(A2) & 15) || lda2 % 4)) return TAGAN_E_UNSUPPORTED;
+  const int passes = (precision & 3) == 1 ? 3 : ((precision & 3) == 3 ? 4 : 1);
+  return tagan_gemm_tma(op, m, n, k, A, lda, B, ldb, bias, e.out0, e.ld_out0, 0, passes, workspace, workspace_bytes,
+                        as_stream(stream), nullptr, A2, lda2, k1, epi);
+}

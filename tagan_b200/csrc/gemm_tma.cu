@@ -142,11 +142,245 @@ struct Params {
   int b_presplit;          // B arrives already split (tmB = hi image, tmB2 = lo image): only A is split in-kernel
   uint32_t idesc;
   float* colsum_part;       // TN only: [splits][2][M] partial column sums of A (the bias gradient), or null
+  int fused;                // the epilogue is epi (a tagan_epilogue mode), not the plain store through C
+  int64_t K1;               // > 0: A is the column concatenation [A (k < K1) | A2 (k >= K1)] (tmA / tmA2), NT only
+  tagan_epilogue epi;       // fused epilogue (mode 0 = plain store / bias / accumulate through C)
 };
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused epilogues (struct tagan_epilogue, include/tagan_b200.h).  An epilogue warp owns 32 rows of the tile; one
+// 32-column chunk of the accumulator goes TMEM -> registers (lane = row) -> padded smem -> registers in the
+// row-contiguous layout: lane holds rows 4*i + (lane >> 3), i = 0..7, columns 4*(lane & 7)..+3 of the chunk, so
+// every global access below is a 128-byte row segment per 8 lanes.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_e(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float4 ld4g(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4g(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ void epi_load_chunk(uint32_t taddr, uint32_t stg, int lane, float4 (&v)[8]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  __syncwarp();                                              // the previous chunk's reads of the staging tile are done
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    sts128(stg + (uint32_t)((lane * EPI_PITCH + j) * 4),
+           make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+  __syncwarp();
+  const uint32_t src0 = stg + (uint32_t)(((lane >> 3) * EPI_PITCH + (lane & 7) * 4) * 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = lds128(src0 + (uint32_t)(i * 4 * EPI_PITCH * 4));
+}
+
+// One 128x128 tile through a fused epilogue; arrives on the accumulator's "empty" barrier as soon as the last
+// tcgen05.ld of the tile has completed (before the second LayerNorm phase), so the MMA warp never waits on the
+// normalisation pass.
+__device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int lane, int acc, int mt, int64_t n0,
+                                               uint32_t epi_u32, uint64_t* tmem_empty_bar) {
+  const tagan_epilogue& e = p.epi;
+  const uint32_t stg = epi_u32 + (uint32_t)(warp * (32 * EPI_PITCH) * 4);
+  const int64_t row0 = (int64_t)mt * BM + warp * 32 + (lane >> 3);
+  const int cl = (lane & 7) * 4;
+  const uint32_t tbase = ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+  if (e.mode == TAGAN_EPI_RES_LN || e.mode == TAGAN_EPI_STORE) {
+    const bool ln = e.mode == TAGAN_EPI_RES_LN && e.gamma != nullptr;
+    float* tmp = e.out1 ? e.out1 : e.out0;
+    const int64_t ldt = e.out1 ? e.ld_out1 : e.ld_out0;
+    float sd[8], sq[8], ks[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sd[i] = 0.f; sq[i] = 0.f; ks[i] = 0.f; }
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      float4 v[8];
+      epi_load_chunk(tbase + (uint32_t)(cc * 32), stg, lane, v);
+      const int64_t c0 = n0 + cc * 32 + cl;
+      const bool cok = c0 < p.N;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cok && p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 rr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t grow = row0 + 4 * (half * 4 + q);
+          rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.in0 != nullptr && cok && grow < p.M) rr[q] = ld4g(e.in0 + grow * e.ld_in0 + c0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = half * 4 + q;
+          const int64_t grow = row0 + 4 * i;
+          const bool ok = cok && grow < p.M;
+          v[i].x += b4.x + rr[q].x; v[i].y += b4.y + rr[q].y; v[i].z += b4.z + rr[q].z; v[i].w += b4.w + rr[q].w;
+          if (ok) st4g(tmp + grow * ldt + c0, v[i]);
+          if (ln) {
+            // shifted single-pass moments: the shift is the row's first element, so the subtraction below cancels the
+            // row mean up to O(std) and var = E[d^2] - E[d]^2 loses no precision
+            if (cc == 0) ks[i] = __shfl_sync(FULL_MASK, v[i].x, lane & ~7);
+            if (ok) {
+              const float dx = v[i].x - ks[i], dy = v[i].y - ks[i], dz = v[i].z - ks[i], dw = v[i].w - ks[i];
+              sd[i] += (dx + dy) + (dz + dw);
+              sq[i] = fmaf(dx, dx, sq[i]); sq[i] = fmaf(dy, dy, sq[i]); sq[i] = fmaf(dz, dz, sq[i]); sq[i] = fmaf(dw, dw, sq[i]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar);
+    if (!ln) return;
+    const float inv_n = 1.f / (float)p.N;
+    float (&mean)[8] = sd;
+    float (&rstd)[8] = sq;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sd[i] += __shfl_xor_sync(FULL_MASK, sd[i], o);
+        sq[i] += __shfl_xor_sync(FULL_MASK, sq[i], o);
+      }
+      const float md = sd[i] * inv_n;
+      rstd[i] = 1.f / sqrtf(fmaxf(sq[i] * inv_n - md * md, 0.f) + 1e-5f);
+      mean[i] = ks[i] + md;
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      const int64_t c0 = n0 + cc * 32 + cl;
+      if (c0 >= p.N) continue;
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.gamma + c0));
+      const float4 be4 = __ldg(reinterpret_cast<const float4*>(e.beta + c0));
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t grow = row0 + 4 * i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow < p.M) v[i] = __ldcg(reinterpret_cast<const float4*>(tmp + grow * ldt + c0));   // written above by this thread
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t grow = row0 + 4 * i;
+        if (grow >= p.M) continue;
+        float4 y;
+        y.x = (v[i].x - mean[i]) * rstd[i] * g4.x + be4.x;
+        y.y = (v[i].y - mean[i]) * rstd[i] * g4.y + be4.y;
+        y.z = (v[i].z - mean[i]) * rstd[i] * g4.z + be4.z;
+        y.w = (v[i].w - mean[i]) * rstd[i] * g4.w + be4.w;
+        st4g(e.out0 + grow * e.ld_out0 + c0, y);
+      }
+    }
+    if ((lane & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t grow = row0 + 4 * i;
+        if (grow < p.M) {
+          if (e.mean) e.mean[grow] = mean[i];
+          if (e.rstd) e.rstd[grow] = rstd[i];
+        }
+      }
+    }
+    return;
+  }
+  // ---- element-wise modes ----
+#pragma unroll 1
+  for (int cc = 0; cc < BN / 32; ++cc) {
+    float4 v[8];
+    epi_load_chunk(tbase + (uint32_t)(cc * 32), stg, lane, v);
+    const int64_t c0 = n0 + cc * 32 + cl;
+    const bool cok = c0 < p.N;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cok && p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 a0[4], a1[4];
+      if (e.mode == TAGAN_EPI_GATES) {
+        const bool rpart = c0 < e.split;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t grow = row0 + 4 * (half * 4 + q);
+          a0[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rpart && cok && grow < p.M) a0[q] = ld4g(e.in0 + grow * e.ld_in0 + c0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = half * 4 + q;
+          const int64_t grow = row0 + 4 * i;
+          if (!(cok && grow < p.M)) continue;
+          float4 s;
+          s.x = sigmoid_e(v[i].x + b4.x); s.y = sigmoid_e(v[i].y + b4.y);
+          s.z = sigmoid_e(v[i].z + b4.z); s.w = sigmoid_e(v[i].w + b4.w);
+          if (rpart) {
+            st4g(e.out0 + grow * e.ld_out0 + c0, s);
+            st4g(e.out1 + grow * e.ld_out1 + c0, make_float4(s.x * a0[q].x, s.y * a0[q].y, s.z * a0[q].z, s.w * a0[q].w));
+          } else {
+            st4g(e.out2 + grow * e.ld_out2 + (c0 - e.split), s);
+          }
+        }
+      } else if (e.mode == TAGAN_EPI_BLEND) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t grow = row0 + 4 * (half * 4 + q);
+          a0[q] = a1[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cok && grow < p.M) { a0[q] = ld4g(e.in0 + grow * e.ld_in0 + c0); a1[q] = ld4g(e.in1 + grow * e.ld_in1 + c0); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = half * 4 + q;
+          const int64_t grow = row0 + 4 * i;
+          if (!(cok && grow < p.M)) continue;
+          float4 t, o;
+          t.x = tanhf(v[i].x + b4.x); t.y = tanhf(v[i].y + b4.y); t.z = tanhf(v[i].z + b4.z); t.w = tanhf(v[i].w + b4.w);
+          o.x = (1.f - a0[q].x) * a1[q].x + a0[q].x * t.x;
+          o.y = (1.f - a0[q].y) * a1[q].y + a0[q].y * t.y;
+          o.z = (1.f - a0[q].z) * a1[q].z + a0[q].z * t.z;
+          o.w = (1.f - a0[q].w) * a1[q].w + a0[q].w * t.w;
+          st4g(e.out0 + grow * e.ld_out0 + c0, t);
+          st4g(e.out1 + grow * e.ld_out1 + c0, o);
+        }
+      } else {                                               // TAGAN_EPI_GATES_BWD
+        float4 a2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t grow = row0 + 4 * (half * 4 + q);
+          a0[q] = a1[q] = a2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cok && grow < p.M) {
+            a0[q] = ld4g(e.in0 + grow * e.ld_in0 + c0);
+            a1[q] = ld4g(e.in1 + grow * e.ld_in1 + c0);
+            a2[q] = ld4g(e.out1 + grow * e.ld_out1 + c0);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = half * 4 + q;
+          const int64_t grow = row0 + 4 * i;
+          if (!(cok && grow < p.M)) continue;
+          const float4 d = v[i], r = a0[q], sc = a1[q];
+          st4g(e.out0 + grow * e.ld_out0 + c0, make_float4(d.x * sc.x * r.x * (1.f - r.x), d.y * sc.y * r.y * (1.f - r.y),
+                                                          d.z * sc.z * r.z * (1.f - r.z), d.w * sc.w * r.w * (1.f - r.w)));
+          st4g(e.out1 + grow * e.ld_out1 + c0, make_float4(a2[q].x + d.x * r.x, a2[q].y + d.y * r.y,
+                                                          a2[q].z + d.z * r.z, a2[q].w + d.w * r.w));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tmem_empty_bar);
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmB2) {
+                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmA2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* raw_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
@@ -197,7 +431,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_arrive_expect_tx(&raw_bar[stage], (p.b_presplit ? 3 : 2) * TILE_BYTES);
           if (!p.a_mn_major) {
-            tma_load_2d(st, &tmA, (int)k0, m0, &raw_bar[stage]);
+            if (p.K1 > 0 && k0 >= p.K1) tma_load_2d(st, &tmA2, (int)(k0 - p.K1), m0, &raw_bar[stage]);
+            else tma_load_2d(st, &tmA, (int)k0, m0, &raw_bar[stage]);
           } else {
 #pragma unroll
             for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &tmA, m0 + 32 * b, (int)k0, &raw_bar[stage]);
@@ -358,6 +593,11 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       const int64_t n0 = (int64_t)nt * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (p.fused) {                                       // warp-uniform
+        epilogue_fused(p, warp, lane, acc, mt, n0, epi_u32, &tmem_empty[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       float* out = p.partial ? p.partial + (int64_t)ks * p.M * p.N : p.C;
       const int64_t ldo = p.partial ? p.N : p.ldc;
       const bool interior = p.c_vec && ((int64_t)(mt + 1) * BM <= p.M) && (n0 + BN <= p.N);
@@ -582,15 +822,32 @@ size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t 
 
 int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                    int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st, float* colsum_a /* TN only, [M] or null */) {
-  static bool attr_set = false;
-  if (!attr_set) {
+                   void* workspace, size_t workspace_bytes, cudaStream_t st, float* colsum_a /* TN only, [M] or null */,
+                   const float* A2, int64_t lda2, int64_t K1, const tagan_epilogue* epi) {
+  // the opt-in to > 48 KB of dynamic shared memory is per device: remember it per device ordinal
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev < 0 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    if (dev >= 0) attr_set[dev] = true;
   }
   Plan pl = make_plan(M, N, K);
   Params p;
+  p.fused = 0;
+  p.K1 = 0;
+  p.epi = tagan_epilogue{};
+  if (epi != nullptr) {
+    if (op == 2 || pl.splits != 1 || colsum_a != nullptr || accumulate) return TAGAN_E_UNSUPPORTED;
+    if (epi->mode == TAGAN_EPI_RES_LN && epi->gamma != nullptr && pl.tiles_n != 1) return TAGAN_E_UNSUPPORTED;
+    p.fused = 1;
+    p.epi = *epi;
+  }
+  if (A2 != nullptr) {
+    if (op != 0 || K1 <= 0 || K1 >= K || (K1 % BK) != 0) return TAGAN_E_UNSUPPORTED;
+    p.K1 = K1;
+  }
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.C = C; p.ldc = ldc;
   p.accumulate = accumulate;
@@ -614,9 +871,12 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   else p.c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | ((uint32_t)p.b_mn_major << 16) |
             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  CUtensorMap tmA, tmB, tmB2;
+  CUtensorMap tmA, tmB, tmB2, tmA2;
   // NT: A[M,K], B[N,K] (K-major).  NN: A[M,K], B[K,N] (MN-major).  TN: A[K,M], B[K,N] (both MN-major).
-  const bool okA = p.a_mn_major ? make_map(&tmA, A, K, M, lda, true, true) : make_map(&tmA, A, M, K, lda, false);
+  bool okA = p.a_mn_major ? make_map(&tmA, A, K, M, lda, true, true)
+                          : make_map(&tmA, A, M, p.K1 > 0 ? p.K1 : K, lda, false);
+  if (p.K1 > 0) okA = okA && make_map(&tmA2, A2, M, K - p.K1, lda2, false);
+  else tmA2 = tmA;
   p.b_presplit = 0;
   bool okB;
   if (want_presplit(op, N, K) && passes != 1) {
@@ -625,9 +885,10 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
     if (!workspace || workspace_bytes < off + 2 * (size_t)rows * ldo * sizeof(float)) return TAGAN_E_WORKSPACE;
     float* hi = reinterpret_cast<float*>(static_cast<char*>(workspace) + off);
     float* lo = hi + rows * ldo;
-    presplit_kernel<<<ceil_div_i64(rows * cols, 256), 256, 0, st>>>(B, rows, cols, ldb, hi, lo, ldo);
     okB = make_map(&tmB, hi, rows, cols, ldo, p.b_mn_major) && make_map(&tmB2, lo, rows, cols, ldo, p.b_mn_major);
     p.b_presplit = 1;
+    // the tensor maps only need addresses: encode them first so that nothing is enqueued when encoding fails
+    if (okA && okB) presplit_kernel<<<ceil_div_i64(rows * cols, 256), 256, 0, st>>>(B, rows, cols, ldb, hi, lo, ldo);
   } else {
     okB = p.b_mn_major ? make_map(&tmB, B, K, N, ldb, true) : make_map(&tmB, B, N, K, ldb, false);
     tmB2 = tmB;
@@ -635,7 +896,7 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   if (!okA || !okB) return TAGAN_E_UNSUPPORTED;
   int64_t work = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits;
   int grid = (int)(work < 148 ? work : 148);
-  gemm_tma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2);
+  gemm_tma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
   if (p.partial)
     tma_splitk_reduce<<<ceil_div_i64(M * N, 256), 256, 0, st>>>(p.partial, pl.splits, M, N, bias, C, ldc, accumulate);
   if (p.colsum_part)

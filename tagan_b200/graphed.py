@@ -48,7 +48,10 @@ class GraphedStep:
     graph runs; step k+1 begins with a device-to-device move staging -> static inputs (sub-millisecond), after
     which the staging set is free again.  Every step still performs exactly one H2D copy of its inputs and one D2H
     read of its loss; the host tensors must hold step k+1's data when ``step()`` for step k is called (the first
-    prefetch is issued by the constructor)."""
+    prefetch is issued by the constructor).  Ownership: the host tensors are read asynchronously by the copy stream
+    after ``launch()``; ``__call__`` waits for that read (``wait_prefetch``) before it returns, so a caller may
+    refill them as soon as it has the loss.  Callers of the asynchronous ``launch()`` must call ``wait_prefetch()``
+    themselves before touching the host tensors."""
 
     def __init__(self, fn: Callable, xs_host: Sequence[torch.Tensor], eis_host: Sequence[torch.Tensor],
                  device: torch.device, warmup: int = 2, prefetch: bool = True,
@@ -150,7 +153,15 @@ class GraphedStep:
         torch.cuda.synchronize(self.device)
         self.graph.reset()
 
+    def wait_prefetch(self) -> None:
+        """Block until the H2D prefetch issued by the last ``launch()`` has read the pinned host tensors.  They belong
+        to ``GraphedStep`` from ``launch()`` until this returns; refill them (step k+2's data) only afterwards."""
+        if self.prefetch:
+            self._h2d_ready.synchronize()
+
     def __call__(self) -> float:
+        """One step; returns the loss.  On return the pinned host tensors are free to be overwritten."""
         self.launch()
         torch.cuda.current_stream().synchronize()
+        self.wait_prefetch()
         return float(self.loss_host)

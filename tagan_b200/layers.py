@@ -2,9 +2,16 @@
 
 Same constructor arguments, parameter names (``state_dict`` keys) and forward signatures as the
 reference classes, so reference checkpoints load unchanged and ``tagan_b200.patch(model)`` can
-swap them into a reference ``TAGAN``.  All arithmetic runs in libtagan_b200.so; dropout is the
-only op left to torch (its RNG cannot be matched, parity is defined at dropout=0 / eval()).
+swap them into a reference ``TAGAN``.  All arithmetic runs in libtagan_b200.so; the OUTPUT dropouts
+(``output_dropout`` / ``dropout_layer``) are the only ops left to torch (their RNG cannot be matched; parity is
+defined at dropout=0 / eval()).
+
+Documented deviation: the reference also applies dropout to the attention WEIGHTS (``attn_dropout``,
+geometric_attention.py:514 and temporal_attention.py:1179).  The fused attention kernels never materialise the
+weights, so that dropout is NOT applied; in train() mode with p > 0 the layers say so once with a ``UserWarning``
+(``attn_dropout`` is kept as a module only so that ``state_dict`` / ``repr`` match).  eval() and p = 0 are exact.
 """
+import warnings
 import math
 from typing import Dict, List, Optional, Tuple, Union
 
@@ -12,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import fused, ops
 
 
 class LayerNorm(nn.LayerNorm):
@@ -62,8 +69,21 @@ class GeometricAttention(nn.Module):
         if hasattr(self, "distance_param"):
             nn.init.constant_(self.distance_param, 1.0 if self.distance_metric == "gaussian_kernel" else 0.1)
 
+    def _warn_attn_dropout(self):
+        if self.training and self.dropout_prob > 0 and not getattr(self, "_warned_attn_dropout", False):
+            self._warned_attn_dropout = True
+            warnings.warn(f"{type(self).__name__}: attention-weight dropout (p={self.dropout_prob}) is not applied by the "
+                          "fused kernel in train() mode; output dropout is.  Use eval() or dropout=0 for reference parity.")
+
+    def _fused_ok(self) -> bool:
+        """Stage-level fused path (fused.geo_layer): LayerNorm on, dropout an identity (eval() or p = 0)."""
+        return ops.FUSION and self.use_layer_norm and not (self.training and self.dropout_prob > 0)
+
     def forward_csr(self, x: torch.Tensor, csr: ops.CSR, return_attention_weights: bool = False):
         """x ``[N,H]`` -> ``[N,H]`` (+ per-entry weights ``[nnz,h]`` aligned with ``csr.row/col``)."""
+        self._warn_attn_dropout()
+        if self._fused_ok() and not return_attention_weights:
+            return fused.geo_layer(self, x, [csr])
         ln = self.use_layer_norm
         xn = ops.layer_norm(x, self.layer_norm1.weight, self.layer_norm1.bias) if ln else x
         w_qkv = torch.cat([self.q_linear.weight, self.k_linear.weight, self.v_linear.weight], 0)
@@ -85,6 +105,9 @@ class GeometricAttention(nn.Module):
         projection, the output projection and LN2 run once over all ``T*N`` rows (one large tcgen05 GEMM each instead
         of T small ones); kernel (a) runs per snapshot on row slices.  Same arithmetic per row as ``forward_csr``."""
         t_steps, n, hdim = x3.shape
+        self._warn_attn_dropout()
+        if self._fused_ok():
+            return fused.geo_layer(self, x3, csrs)
         rows = x3.reshape(t_steps * n, hdim)
         ln = self.use_layer_norm
         xn = ops.layer_norm(rows, self.layer_norm1.weight, self.layer_norm1.bias) if ln else rows
@@ -329,6 +352,10 @@ class AsymmetricTemporalAttention(nn.Module):
                 return_attention_weights: bool = False, time_major: bool = False):
         """``time_major=True`` (extension): ``x`` is the physical ``[T,B,H]`` stack of the per-snapshot tensors, i.e.
         what the list form is turned into anyway -- saves the stack copy; the result is the same ``[B,T,H]`` view."""
+        if self.training and self.dropout_prob > 0 and not getattr(self, "_warned_attn_dropout", False):
+            self._warned_attn_dropout = True
+            warnings.warn(f"AsymmetricTemporalAttention: attention-weight dropout (p={self.dropout_prob}) is not applied by "
+                          "the fused kernel in train() mode; output dropout is.  Use eval() or dropout=0 for reference parity.")
         if time_major and isinstance(x, torch.Tensor):
             phys = x.contiguous()
             t, b, hdim = phys.shape
@@ -346,10 +373,13 @@ class AsymmetricTemporalAttention(nn.Module):
         dev = phys.device
         ln = self.use_layer_norm
         rows = phys.reshape(-1, hdim)
-        xn = ops.layer_norm(rows, self.layer_norm1.weight, self.layer_norm1.bias) if ln else rows
-        w_qkv = torch.cat([self.q_linear.weight, self.k_linear.weight, self.v_linear.weight], 0)
-        b_qkv = torch.cat([self.q_linear.bias, self.k_linear.bias, self.v_linear.bias], 0)
-        qkv = ops.linear(xn, w_qkv, b_qkv)
+        use_fused = (ops.FUSION and ln and not return_attention_weights
+                     and not (self.training and self.dropout_prob > 0))
+        if not use_fused:
+            xn = ops.layer_norm(rows, self.layer_norm1.weight, self.layer_norm1.bias) if ln else rows
+            w_qkv = torch.cat([self.q_linear.weight, self.k_linear.weight, self.v_linear.weight], 0)
+            b_qkv = torch.cat([self.q_linear.bias, self.k_linear.bias, self.v_linear.bias], 0)
+            qkv = ops.linear(xn, w_qkv, b_qkv)
         bias = self._position_bias(t, dev)
         ts = None
         if self.time_aware and time_stamps is not None:
@@ -364,6 +394,9 @@ class AsymmetricTemporalAttention(nn.Module):
                     raise NotImplementedError("per-node timestamps at this size are not supported yet")
                 bias = bias.unsqueeze(0) + self._time_bias(ts)
         tmask = self._resolve_mask(attention_mask, ts, b, t, dev)
+        if use_fused:
+            out = fused.tattn_layer(self, rows, bias, tmask, b, t, time_major).view(phys.shape)
+            return out.permute(1, 0, 2) if time_major else out
         ctx, attn = ops.temporal_attention_core(qkv, bias, tmask, b, t, self.num_heads, time_major,
                                                 want_attn=return_attention_weights)
         o = ops.linear(ctx, self.output_proj.weight, self.output_proj.bias)
@@ -479,6 +512,9 @@ class TemporalEvolutionLayer(nn.Module):
         """xs3 ``[T,N,in]`` -> ``[T,N,hidden]`` (:648-755)."""
         t_steps, n, _ = xs3.shape
         ts = time_stamps.float().contiguous() if time_stamps is not None else None
+        if (ops.FUSION and not self.bidirectional and self.use_layer_norm and not (self.training and self.dropout > 0)
+                and fused.evolution_supported(self.input_dim, self.hidden_dim)):
+            return fused.evolution(self, xs3, ts)
         def stacked(v):
             return v if isinstance(v, torch.Tensor) else torch.stack(v)
         fwd = stacked(self._scan(self.forward_cell, xs3, ts, list(range(t_steps)), False))
@@ -527,6 +563,8 @@ class TemporalSkipConnection(nn.Module):
     def forward_stacked(self, e3: torch.Tensor) -> torch.Tensor:
         """e3 ``[T,N,in]`` -> ``[T,N,in]`` (:846-946)."""
         t_steps, n, _ = e3.shape
+        if fused.skip_supported(self, t_steps, n) and not (self.training and self.dropout > 0):
+            return fused.skip_connection(self, e3)
         rows = e3.reshape(t_steps * n, -1)
         p = ops.linear(rows, self.input_proj.weight, self.input_proj.bias)
         if self.apply_activation:
@@ -628,7 +666,13 @@ class TemporalPropagation(nn.Module):
         e = self.evolution_layer.forward_stacked(x3, time_stamps)
         if self.use_skip_connection:
             e = self.skip_connection.forward_stacked(e)
+        return self._tail(e)
+
+    def _tail(self, e: torch.Tensor) -> torch.Tensor:
+        """``layer_norm(dropout(output_proj(e)))`` (:1487-1500), e ``[T,N,H]``."""
         t_steps, n, _ = e.shape
+        if ops.FUSION and self.use_layer_norm and not (self.training and self.dropout > 0):
+            return fused.proj_ln(e, self.output_proj, self.layer_norm)
         o = ops.linear(e.reshape(t_steps * n, -1), self.output_proj.weight, self.output_proj.bias)
         o = self.dropout_layer(o)
         g, b = _ln_args(self, "layer_norm", self.use_layer_norm)
@@ -666,11 +710,7 @@ class TemporalPropagation(nn.Module):
             memory_bank.update(ids_d, cur.detach() + (0.01 * t if t > 0 else 0.0), t)
             outs.append(cur)
         e = torch.stack(outs, 0)
-        t_steps, n, _ = e.shape
-        o = ops.linear(e.reshape(t_steps * n, -1), self.output_proj.weight, self.output_proj.bias)
-        o = self.dropout_layer(o)
-        g, b = _ln_args(self, "layer_norm", self.use_layer_norm)
-        return ops.layer_norm(o, g, b).view(t_steps, n, self.hidden_dim)
+        return self._tail(e)
 
     def forward(self, node_features_seq, node_masks_seq=None, time_stamps=None, memory_bank=None):
         ids_given = (isinstance(node_masks_seq, list) and len(node_masks_seq) > 0

@@ -126,6 +126,10 @@ class NodeMemoryBank:
         states = _f32c(states.to(self.device))
         if states.dim() == 1:
             states = states.unsqueeze(0)
+        if states.dim() != 2 or states.shape[1] != self.hidden_dim:
+            raise ValueError(f"NodeMemoryBank.update: states must be [M, {self.hidden_dim}], got {tuple(states.shape)}")
+        if states.untyped_storage().data_ptr() == self.table.untyped_storage().data_ptr():
+            states = states.clone()            # a view of the table (e.g. an old get_state row): the kernels assume no aliasing
         ids = self._slots(node_ids)
         m = ids.numel()
         lds = states.stride(0) if states.shape[0] > 1 else self.hidden_dim
@@ -160,7 +164,7 @@ class NodeMemoryBank:
         s = self._slot_of_key(node_id)
         if s is None or not bool(self.valid[s].item()):
             return None
-        return self.table[s]
+        return self.table[s].clone()           # the reference hands out a tensor that later updates replace, never mutate
 
     def update_state(self, node_id, state: torch.Tensor, timestep: int = 0):
         self.update([node_id], state.unsqueeze(0), timestep)          # :235-244
@@ -185,7 +189,8 @@ class NodeMemoryBank:
     # dict-style views of the reference attributes (host copies; for inspection / pickling only)
     @property
     def node_states(self) -> Dict[Any, torch.Tensor]:
-        return {self._key(int(s)): self.table[s] for s in torch.nonzero(self.valid).flatten().tolist()}
+        snap = self.table.clone()              # detached snapshot: later updates / decay must not mutate what was handed out
+        return {self._key(int(s)): snap[s] for s in torch.nonzero(self.valid).flatten().tolist()}
 
     @property
     def inactivity_counter(self) -> Dict[Any, int]:

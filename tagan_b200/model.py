@@ -87,7 +87,8 @@ def patch(model: nn.Module) -> nn.Module:
 
     Keeps every parameter (state_dict keys are identical) and the reference's own ``forward``:
     ``model.geometric_attention_layers[i]``, ``model.temporal_propagation``, ``model.temporal_attention``
-    and ``model.memory_bank`` (model.py:57-61, 73-113 of the reference) are replaced.
+    and ``model.memory_bank`` (model.py:57-61, 73-113 of the reference) are replaced.  Every swapped module takes the
+    train()/eval() mode of the module it replaces, so ``model.eval(); patch(model)`` stays deterministic.
     """
     cfg = model.config
     dev = next(model.parameters()).device
@@ -97,24 +98,29 @@ def patch(model: nn.Module) -> nn.Module:
         new = TAGANGraphAttention(cfg.hidden_dim, cfg.num_heads, cfg.dropout, metric, cfg.use_layer_norm,
                                   cfg.learnable_distance)
         new.load_state_dict(old.state_dict())
-        new_layers.append(new.to(dev))
+        new_layers.append(new.to(dev).train(old.training))
     model.geometric_attention_layers = new_layers
     tp = TemporalPropagation(cfg.hidden_dim, cfg.hidden_dim, cfg.dropout, cfg.time_aware, cfg.bidirectional,
                              cfg.use_layer_norm, cfg.use_skip_connection, cfg.use_gating, cfg.temporal_window_size,
                              cfg.aggregation_method, cfg.use_residual)
     tp.load_state_dict(model.temporal_propagation.state_dict())
-    model.temporal_propagation = tp.to(dev)
+    model.temporal_propagation = tp.to(dev).train(model.temporal_propagation.training)
     ta = AsymmetricTemporalAttention(cfg.hidden_dim, cfg.num_heads, cfg.dropout, causal=cfg.causal_attention,
                                      time_aware=True, use_layer_norm=cfg.use_layer_norm,
                                      asymmetric_window_size=cfg.window_size,
                                      relative_position_bias=cfg.asymmetric_temporal_bias)
     ta.load_state_dict(model.temporal_attention.state_dict())
-    model.temporal_attention = ta.to(dev)
+    model.temporal_attention = ta.to(dev).train(model.temporal_attention.training)
     if getattr(model, "skip_layer_norm", None) is not None:                          # row a5 (model.py:258-262)
         ln = LayerNorm(cfg.hidden_dim)
         ln.load_state_dict(model.skip_layer_norm.state_dict())
-        model.skip_layer_norm = ln.to(dev)
+        model.skip_layer_norm = ln.to(dev).train(model.skip_layer_norm.training)
     if dev.type == "cuda":      # (on CPU only the module swap is done; the kernels need a CUDA device to run)
+        old_bank = getattr(model, "memory_bank", None)
+        if old_bank is not None and len(getattr(old_bank, "node_states", {})) > 0:
+            import warnings
+            warnings.warn("tagan_b200.patch: the model's memory bank holds %d node states; they are NOT migrated to the "
+                          "device bank (the reference model never reads them: SURVEY.md fact 5)" % len(old_bank.node_states))
         model.memory_bank = NodeMemoryBank(cfg.hidden_dim, decay_factor=0.8, max_inactivity=cfg.temporal_window_size,
                                            device=dev)
     return model

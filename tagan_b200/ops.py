@@ -19,6 +19,10 @@ METRIC_ID = {m: i for i, m in enumerate(METRICS)}
 # 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = 1xTF32 tcgen05
 GEMM_PRECISION = 1
 
+# stage-level fusion (tagan_b200/fused.py): fused GEMM epilogues, fused row passes, in-place residual gradients.
+# False = the op-by-op composition of the stand-alone kernels (kept for dropout > 0 in training and as a test reference)
+FUSION = True
+
 # number of libtagan_b200 kernels launched (bench.py reports `gpu_launches` from this)
 CALLS = {"n": 0}
 
@@ -28,8 +32,12 @@ PROFILE = None
 
 
 class _timed:
-    def __init__(self, name):
+    """Bracket a library call with CUDA events on the launching stream when ``PROFILE`` is a dict; ``nbytes`` = the
+    call's algorithmic bytes (recorded beside the events so bench.py can quote GB/s per kernel family)."""
+
+    def __init__(self, name, nbytes=0):
         self.name = name
+        self.nbytes = nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -41,7 +49,7 @@ class _timed:
     def __exit__(self, *a):
         if PROFILE is not None:
             self.e.record(torch.cuda.current_stream())
-            PROFILE.setdefault(self.name, []).append((self.s, self.e))
+            PROFILE.setdefault(self.name, []).append((self.s, self.e, self.nbytes))
 
 
 def _ptr(t):
@@ -197,7 +205,7 @@ def gemm(op: int, m: int, n: int, k: int, a, lda, b, ldb, bias, c, ldc, accumula
     nbytes = lib.tagan_gemm_workspace_bytes(op, m, n, k)
     dev = c.device if isinstance(c, torch.Tensor) else torch.device("cuda", torch.cuda.current_device())
     ws = workspace(nbytes, dev) if nbytes else None
-    with _timed("gemm"):
+    with _timed("gemm", 4 * (m * k + n * k + m * n * (2 if accumulate else 1))):
         rc = lib.tagan_gemm(op, m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(bias), _ptr(c), ldc, int(accumulate),
                             GEMM_PRECISION, _ptr(ws), ws.numel() if ws is not None else 0, _stream())
     _lib.check(rc, "tagan_gemm")
@@ -222,7 +230,7 @@ def gemm_tn_colsum(m: int, n: int, k: int, a, lda, b, ldb, c, ldc) -> torch.Tens
     out = torch.empty(m, dtype=torch.float32, device=dev)
     nbytes = lib.tagan_gemm_tn_colsum_workspace_bytes(m, n, k)
     ws = workspace(nbytes, dev)
-    with _timed("gemm"):
+    with _timed("gemm", 4 * (m * k + n * k + m * n)):
         rc = lib.tagan_gemm_tn_colsum(m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(c), ldc, _ptr(out), GEMM_PRECISION,
                                       _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "tagan_gemm_tn_colsum")
