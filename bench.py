@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--e2e-no-prefetch", action="store_true",
                     help="e2e arm: H2D copies inside the step's graph instead of prefetching the next step's inputs")
     ap.add_argument("--no-bank", action="store_true")
+    ap.add_argument("--no-partitioned", action="store_true",
+                    help="N >= 2: skip the node-partitioned config-4 block that follows the data-parallel measurement")
     ap.add_argument("--cuda-profiler", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     return ap.parse_args()
@@ -170,6 +172,153 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+
+# ------------------------------------------------------------------------------------------
+# single large graph, node-partitioned (config 4): snapshot-parallel geometric stage + node-parallel temporal stages
+# ------------------------------------------------------------------------------------------
+def partitioned_snapshots(w, world):
+    """Largest T <= w.snapshots with T % world == 0 that fits 180 GB per rank: the saved activations are about
+    8.3 [N,H] tensors per local snapshot (geometric) + 35 [T,N/world,H] tensors (temporal stages)."""
+    t = w.snapshots
+    while t > world:
+        per_rank = (t / world * 8.3 + t / world * 35) * w.num_nodes * w.hidden * 4 / 1e9
+        if t % world == 0 and per_rank < 120:
+            return t
+        t -= 1
+    return world
+
+
+def run_partitioned(w, metric, world, rank, dev, steps, warmup, no_bank=False, want_e2e=True):
+    """One TAGAN layer fwd+bwd on ONE graph of w.num_nodes nodes over `world` GPUs (tagan_b200.partitioned.
+    forward_snapshot_parallel).  Inputs are generated on the device (16 GB of host randn would dominate the run)."""
+    import torch.distributed as dist
+    import tagan_b200
+    from tagan_b200 import fused, ops, partitioned
+    from tagan_b200.dist import GradBucket, NodePartition
+    n, e, hdim, heads = w.num_nodes, w.num_edges, w.hidden, w.heads
+    t_steps = partitioned_snapshots(w, world)
+    t_loc = t_steps // world
+    part = NodePartition(n, world)
+    lo, hi = part.bounds(rank)
+    n_loc = hi - lo
+    comm = partitioned.AllToAllComm(world)
+
+    # parity on a small graph first: partitioned == unpartitioned (forward bit-identical on every rank)
+    torch.manual_seed(0)
+    par = None
+    if world > 1:
+        pn, pe, ph, pheads, pt = 64 * world, 3000, 64, 4, 2 * world
+        small = tagan_b200.TAGANLayer(ph, pheads, metric).to(dev)
+        g = torch.Generator().manual_seed(5)
+        pxs = torch.randn(pt, pn, ph, generator=g).to(dev)
+        peis = [torch.randint(0, pn, (2, pe), generator=g).to(dev) for _ in range(pt)]
+        pts = torch.arange(pt, dtype=torch.float32, device=dev).expand(pn, pt)
+        full = small(list(pxs.unbind(0)), peis, pts)
+        plo, phi = NodePartition(pn, world).bounds(rank)
+        loc = partitioned.forward_snapshot_parallel(small, pxs[:, plo:phi].contiguous(), peis[rank * 2:(rank + 1) * 2],
+                                                    NodePartition(pn, world), rank, comm, pts[plo:phi])
+        same = torch.tensor([1.0 if torch.equal(loc, full[plo:phi]) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        par = {"forward_bit_identical_to_unpartitioned": bool(same.item() == 1.0), "nodes": pn, "snapshots": pt}
+        del small, full, loc
+
+    torch.manual_seed(0)
+    layer = tagan_b200.TAGANLayer(hdim, heads, metric).to(dev)
+    layer.geometric.validate_indices = False
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    x_loc = torch.randn(t_steps, n_loc, hdim, device=dev, generator=gen)
+    my_eis = []
+    for t in range(rank * t_loc, (rank + 1) * t_loc):                # the global edge list of snapshot t is a function of t only
+        ge = torch.Generator(device=dev).manual_seed(7000 + t)
+        my_eis.append(torch.randint(0, n, (2, e), device=dev, generator=ge))
+    ts_loc = torch.arange(t_steps, dtype=torch.float32, device=dev).expand(n_loc, t_steps)
+    bank = None
+    if not no_bank:
+        bank = tagan_b200.NodeMemoryBank(hdim, 0.8, 3, device=dev, capacity=n_loc)
+        bank.check_range = False
+    bucket = GradBucket(list(layer.parameters())) if world > 1 else None
+
+    def step(x, eis):
+        layer.zero_grad(set_to_none=True)
+        out = partitioned.forward_snapshot_parallel(layer, x, eis, part, rank, comm, ts_loc, bank)
+        loss = fused.mean_square(out.permute(1, 0, 2))
+        loss.backward()
+        if world > 1:
+            bucket.all_reduce(world)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        step(x_loc, my_eis)
+    barrier()
+    torch.cuda.reset_peak_memory_stats()
+    ops.CALLS["n"] = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step(x_loc, my_eis)
+    ev1.record()
+    barrier()
+    launches = ops.CALLS["n"]
+    tms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms.item()) / steps
+    units = e * t_steps
+    res = {"workload": w.name, "nodes": n, "edges_per_snapshot": e, "snapshots": t_steps, "snapshots_of": w.snapshots,
+           "hidden": hdim, "heads": heads, "ms_per_step": ms_step, "value": units / (ms_step * 1e-3), "unit": UNIT,
+           "mode": "snapshot-parallel geometric stage (%d snapshots per GPU, full CSR, no halo) + 2 all-to-alls per direction "
+                   "+ node-parallel GRU / skip / temporal attention / bank (%d nodes per GPU); weight-gradient all-reduce; "
+                   "eager launches" % (t_loc, n_loc),
+           "a2a_bytes_per_rank_per_exchange": (world - 1) * t_loc * n_loc * hdim * 4,
+           "peak_mem_gb_per_rank": torch.cuda.max_memory_allocated() / 1e9, "gpu_launches": launches, "parity": par}
+    # whole-layer byte budget of SURVEY.md section 8d (same formula as the data-parallel line), summed over all ranks
+    nnz = e + n                                                       # upper bound (duplicates are rare on a uniform graph)
+    bytes_a = nnz * (6 * hdim * 4 + 16) + n * (8 * hdim * 4 + 16 * heads + 16)
+    wl = t_steps * bytes_a + 73 * hdim * 4 * n * t_steps + 11 * t_steps * hdim * 4 * n
+    if not no_bank:
+        wl += t_steps * n * ((2 * hdim * 4 + 4) + (3 * hdim * 4 + 16) + (2 * hdim * 4 + 8))
+    peak, _ = peaks()
+    res["whole_layer_roofline"] = {"algorithmic_gb_per_step": wl / 1e9, "achieved_gbs_all_ranks": wl / 1e9 / (ms_step * 1e-3),
+                                   "frac_of_n_gpus_hbm": wl / 1e9 / (ms_step * 1e-3) / (peak * world)}
+    if want_e2e:
+        # end to end: this rank's inputs start in pinned host memory every step (H2D inside the timed region), loss read back
+        xh = torch.empty(x_loc.shape, dtype=torch.float32).pin_memory()
+        xh.copy_(x_loc)
+        eh = [torch.empty(ei.shape, dtype=torch.int64).pin_memory() for ei in my_eis]
+        for a, b in zip(eh, my_eis):
+            a.copy_(b)
+        xd, ed = torch.empty_like(x_loc), [torch.empty_like(ei) for ei in my_eis]
+
+        def e2e_step():
+            xd.copy_(xh, non_blocking=True)
+            for a, b in zip(ed, eh):
+                a.copy_(b, non_blocking=True)
+            return float(step(xd, ed).item())
+        e2e_step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(steps):
+            last = e2e_step()
+        g1.record()
+        barrier()
+        ems = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        h2d = xh.numel() * 4 + sum(a.numel() * 8 for a in eh)
+        res["e2e"] = {"value": units / (float(ems.item()) / steps * 1e-3), "unit": UNIT, "ms_per_step": float(ems.item()) / steps,
+                      "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world, "loss": last,
+                      "mode": "eager: per-rank H2D of its node slice (all snapshots) and of its snapshots' edge lists, step, loss D2H"}
+    del layer, x_loc, my_eis, bank
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch.distributed as dist
     import tagan_b200
@@ -185,6 +334,35 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = synth.WORKLOADS[args.workload]
+    if args.workload == "c4":
+        # the north-star configuration: ONE graph of 1M nodes, node-partitioned (does not fit one GPU at T=16: runs the
+        # largest snapshot count that does, and says so)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        res = run_partitioned(w, args.metric, world, rank, dev, args.steps, args.warmup, args.no_bank, not args.no_e2e)
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (generated on device)",
+                    "config": {"workload": w.name, "nodes": res["nodes"], "edges_per_snapshot": res["edges_per_snapshot"],
+                               "snapshots": res["snapshots"], "snapshots_of": res["snapshots_of"], "hidden": res["hidden"],
+                               "heads": res["heads"], "distance_metric": args.metric, "parallelism": res["mode"],
+                               "memory_bank": not args.no_bank,
+                               "l2": "inputs larger than L2 (K and V of one snapshot are 1 GB each)"},
+                    "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peaks()[0], "achieved": res["whole_layer_roofline"]["achieved_gbs_all_ranks"] / world,
+                                 "frac": res["whole_layer_roofline"]["frac_of_n_gpus_hbm"], "traffic": None,
+                                 "kernel": "whole layer, per GPU (SURVEY 8d byte budget / step time / n_gpus)",
+                                 "whole_layer": res["whole_layer_roofline"]},
+                    "cpu_baseline": None, "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"], "clocks": clocks,
+                    "node_partitioned": res}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     t_steps, n, e, hdim = w.snapshots, w.num_nodes, w.num_edges, w.hidden
 
     # synthetic inputs: pinned host copies (e2e arm) and resident device copies (kernel arm)
@@ -434,6 +612,17 @@ def run_ours(args):
         cpu = {"value": cunits / cdt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": cdesc,
                "seconds": cdt, "protocol": "1 warm-up + median of 3"}
 
+    # ---- N >= 2: the node-partitioned single-graph mode (config 4) on the snapshot count that fits, in the same line ----
+    node_part = None
+    if world > 1 and not args.no_partitioned and args.workload == "c3":
+        del layer, xs_d, eis_d, xs_h, eis_h, bank
+        torch.cuda.empty_cache()
+        try:
+            node_part = run_partitioned(synth.WORKLOADS["c4"], args.metric, world, rank, dev, min(args.steps, 3), 3,
+                                        args.no_bank, want_e2e=False)
+        except Exception as exc:  # noqa: BLE001
+            node_part = {"error": str(exc).splitlines()[0][:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -448,7 +637,7 @@ def run_ours(args):
                                       "fit L2, so kernel (a)'s gathers are L2 hits" if n * hdim * 8 < 100e6
                                       else "do not fit L2"))},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "timing": {"mode": timing_mode, "eager_ms_per_step": eager_ms_step}}
+                "timing": {"mode": timing_mode, "eager_ms_per_step": eager_ms_step}, "node_partitioned": node_part}
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:

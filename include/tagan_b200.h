@@ -258,12 +258,26 @@ int tagan_window_gelu_fwd(const float* p, float* out, int32_t T, int64_t inner, 
                           tagan_stream_t stream);
 int tagan_window_gelu_bwd(const float* dgg, const float* p, float* dp, int32_t T, int64_t inner, int32_t window,
                           int32_t agg, tagan_stream_t stream);
-/* GRU blend backward (autograd of temporal_propagation.py:538-542) writing the gate pre-activation gradients into
- * their column slices of the step's [rows,3H] gradient tile: dgz = dhn*(cand-hhat)*z(1-z), dgc = dhn*z*(1-cand^2),
- * dhh = dhn*(1-z). */
-int tagan_gru_blend_bwd(const float* dhn, const float* z, const float* cand, const float* hhat, int64_t ldhh,
-                        float* dgz, float* dgc, int64_t lddg, float* dhh, int64_t lddhh, int64_t rows, int32_t H,
-                        tagan_stream_t stream);
+/* GRU step with the blend fused into the LayerNorm pair (one pass per step and direction):
+ *   forward:  cand = tanh(cand_pre); hn = (1-z) hhat_cur + z cand (temporal_propagation.py:538-542), then as
+ *             tagan_ln_pair_fwd on hn (hn itself is never stored).
+ *   backward: rebuilds hn from (cand, z, hhat_cur), runs tagan_ln_pair_bwd and the autograd of the blend:
+ *             dgz = dhn (cand-hhat) z(1-z), dgc = dhn z (1-cand^2) (column slices of the step's [rows,3H] gradient
+ *             tile, leading dimension lddg), dhh_cur = dhn (1-z).
+ * tagan_gru_reset_bwd: dgr = drs * hhat * r(1-r); dhh += drs * r   (autograd of :531-538, drs = d(r*hhat)). */
+int tagan_gru_blend_ln_fwd(const float* cand_pre, int64_t ldc, const float* z, const float* hhat_cur, int64_t ldcur,
+                           float* cand, const float* gamma_o, const float* beta_o, const float* gamma_h,
+                           const float* beta_h, const float* ts, int64_t ldts, int32_t t_hi, float* s, int64_t lds,
+                           float* hhat_next, int64_t ldhh, float* mean_o, float* rstd_o, float* mean_h, float* rstd_h,
+                           float* decay, int64_t rows, int32_t cols, tagan_stream_t stream);
+int tagan_gru_blend_ln_bwd(const float* ds_ext, int64_t ldds, const float* dhh_next, int64_t lddhh, const float* cand,
+                           const float* z, const float* hhat_cur, int64_t ldcur, float* dgz, float* dgc, int64_t lddg,
+                           float* dhh_cur, int64_t lddcur, const float* gamma_o, const float* beta_o,
+                           const float* gamma_h, const float* mean_o, const float* rstd_o, const float* mean_h,
+                           const float* rstd_h, const float* decay, float* daffine, int32_t accumulate, void* workspace,
+                           size_t workspace_bytes, int64_t rows, int32_t cols, tagan_stream_t stream);
+int tagan_gru_reset_bwd(const float* drs, const float* r, const float* hhat, int64_t ldhh, float* dgr, int64_t lddg,
+                        float* dhh, int64_t lddhh, int64_t rows, int32_t H, tagan_stream_t stream);
 size_t tagan_mse_workspace_bytes(void);
 int tagan_mse_fwd(const float* x, int64_t n, float* loss, void* workspace, size_t workspace_bytes, tagan_stream_t stream);
 int tagan_mse_bwd(const float* x, int64_t n, const float* dloss, float* dx, tagan_stream_t stream);

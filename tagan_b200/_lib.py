@@ -67,7 +67,11 @@ SIGNATURES = {
     "tagan_gelu_ln_bwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _sz, _i64, _i32, _p]),
     "tagan_window_gelu_fwd": (_i32, [_p, _p, _i32, _i64, _i32, _i32, _p]),
     "tagan_window_gelu_bwd": (_i32, [_p, _p, _p, _i32, _i64, _i32, _i32, _p]),
-    "tagan_gru_blend_bwd": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
+    "tagan_gru_blend_ln_fwd": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _i64, _p, _i64, _p, _p,
+                                      _p, _p, _p, _i64, _i32, _p]),
+    "tagan_gru_blend_ln_bwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p,
+                                      _p, _p, _i32, _p, _sz, _i64, _i32, _p]),
+    "tagan_gru_reset_bwd": (_i32, [_p, _p, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "tagan_mse_workspace_bytes": (_sz, []),
     "tagan_mse_fwd": (_i32, [_p, _i64, _p, _p, _sz, _p]),
     "tagan_mse_bwd": (_i32, [_p, _i64, _p, _p, _p]),

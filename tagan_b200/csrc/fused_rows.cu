@@ -121,7 +121,8 @@ reduce_cols_kernel(const float* __restrict__ partial, int parts, int width, floa
 // ---------------------------------------------------------------------------------------------------------------
 template <int NV, bool VEC>
 __global__ void __launch_bounds__(RW * 32)
-ln_pair_fwd_kernel(const float* __restrict__ hn, int64_t ldhn, const float* __restrict__ go, const float* __restrict__ bo,
+ln_pair_fwd_kernel(const float* __restrict__ hn, int64_t ldhn, const float* __restrict__ bz, const float* __restrict__ bbase,
+                   int64_t ldbase, float* __restrict__ cand_out, const float* __restrict__ go, const float* __restrict__ bo,
                    const float* __restrict__ gh, const float* __restrict__ bh, const float* __restrict__ ts, int64_t ldts,
                    int t_hi, float* __restrict__ s, int64_t lds, float* __restrict__ hh, int64_t ldhh,
                    float* __restrict__ mean_o, float* __restrict__ rstd_o, float* __restrict__ mean_h,
@@ -132,6 +133,18 @@ ln_pair_fwd_kernel(const float* __restrict__ hn, int64_t ldhn, const float* __re
   if (row >= rows) return;
   float v[R::E], g[R::E], b[R::E];
   R::load(v, hn + row * ldhn, lane, cols);
+  if (bz != nullptr) {
+    // blend prologue: the row handed in is the candidate PRE-activation; cand = tanh(.), hn = (1-z) h^ + z cand (:538-542)
+    R::load(g, bz + row * (int64_t)cols, lane, cols);
+    R::load(b, bbase + row * ldbase, lane, cols);
+#pragma unroll
+    for (int e = 0; e < R::E; ++e) {
+      const float t = tanhf(v[e]);
+      v[e] = R::valid(e, lane, cols) ? (1.f - g[e]) * b[e] + g[e] * t : 0.f;
+      g[e] = t;
+    }
+    R::store(cand_out + row * (int64_t)cols, g, lane, cols);
+  }
   R::load(g, go, lane, cols);
   R::load(b, bo, lane, cols);
   float mu, rs;
@@ -160,7 +173,9 @@ ln_pair_fwd_kernel(const float* __restrict__ hn, int64_t ldhn, const float* __re
 template <int NV, bool VEC>
 __global__ void __launch_bounds__(RW * 32)
 ln_pair_bwd_kernel(const float* __restrict__ ds_ext, int64_t ldds, const float* __restrict__ dhh, int64_t lddhh,
-                   const float* __restrict__ hn, int64_t ldhn, const float* __restrict__ go, const float* __restrict__ bo,
+                   const float* __restrict__ hn, int64_t ldhn, const float* __restrict__ bz, const float* __restrict__ bbase,
+                   int64_t ldbase, float* __restrict__ dgz, float* __restrict__ dgc, int64_t lddg, float* __restrict__ dbase,
+                   int64_t lddbase, const float* __restrict__ go, const float* __restrict__ bo,
                    const float* __restrict__ gh, const float* __restrict__ mean_o, const float* __restrict__ rstd_o,
                    const float* __restrict__ mean_h, const float* __restrict__ rstd_h, const float* __restrict__ decay,
                    float* __restrict__ dhn, int64_t lddhn, float* __restrict__ partial, int64_t rows, int cols,
@@ -183,6 +198,13 @@ ln_pair_bwd_kernel(const float* __restrict__ ds_ext, int64_t ldds, const float* 
   for (int64_t row = r0 + w; row < r1; row += RW) {
     float xo[R::E], ds[R::E];
     R::load(xo, hn + row * ldhn, lane, cols);
+    float zv[R::E], bv[R::E], cv[R::E];
+    if (bz != nullptr) {                       // blend fused: the row handed in is cand; hn is rebuilt, never stored
+      R::load(zv, bz + row * (int64_t)cols, lane, cols);
+      R::load(bv, bbase + row * ldbase, lane, cols);
+#pragma unroll
+      for (int e = 0; e < R::E; ++e) { cv[e] = xo[e]; xo[e] = (1.f - zv[e]) * bv[e] + zv[e] * cv[e]; }
+    }
     if (ds_ext != nullptr) R::load(ds, ds_ext + row * ldds, lane, cols);
     else {
 #pragma unroll
@@ -229,7 +251,21 @@ ln_pair_bwd_kernel(const float* __restrict__ ds_ext, int64_t ldds, const float* 
     float o[R::E];
 #pragma unroll
     for (int e = 0; e < R::E; ++e) o[e] = rso * (ds[e] * g_o[e] - t1 - xo[e] * t2);
-    R::store(dhn + row * lddhn, o, lane, cols);
+    if (bz == nullptr) {
+      R::store(dhn + row * lddhn, o, lane, cols);
+    } else {
+      // autograd of :538-542 on dhn = o: d z_pre = dhn (cand - h^) z(1-z); d cand_pre = dhn z (1 - cand^2); d h^ = dhn (1-z)
+      float a[R::E];
+#pragma unroll
+      for (int e = 0; e < R::E; ++e) a[e] = o[e] * (cv[e] - bv[e]) * zv[e] * (1.f - zv[e]);
+      R::store(dgz + row * lddg, a, lane, cols);
+#pragma unroll
+      for (int e = 0; e < R::E; ++e) a[e] = o[e] * zv[e] * (1.f - cv[e] * cv[e]);
+      R::store(dgc + row * lddg, a, lane, cols);
+#pragma unroll
+      for (int e = 0; e < R::E; ++e) a[e] = o[e] * (1.f - zv[e]);
+      R::store(dbase + row * lddbase, a, lane, cols);
+    }
   }
   block_partials<NV, VEC, 4>(acc, red, partial, cols);
 }
@@ -426,25 +462,22 @@ __global__ void scale_by_dev_scalar_kernel(const float* __restrict__ x, const fl
     for (int64_t j = n4 * 4; j < n; ++j) out[j] = x[j] * c;
 }
 
-// GRU blend backward writing gate PRE-activation gradients straight into their slices of the step's [rows,3H]
-// gradient tile: dgz = dhn*(cand-h^)*z(1-z), dgc = dhn*z*(1-cand^2), dhh = dhn*(1-z)   (autograd of :538-542)
-__global__ void gru_blend_bwd_kernel(const float* __restrict__ dhn, const float* __restrict__ z, const float* __restrict__ cand,
-                                     const float* __restrict__ hh, int64_t ldhh, float* __restrict__ dgz, float* __restrict__ dgc,
-                                     int64_t lddg, float* __restrict__ dhh, int64_t lddhh, int64_t rows, int H4) {
+// reset-gate backward of the GRU step: dg_r = d(rs) h^ r(1-r); dhh += d(rs) r        (autograd of :531-538)
+__global__ void gru_reset_bwd_kernel(const float* __restrict__ drs, const float* __restrict__ r, const float* __restrict__ hh,
+                                     int64_t ldhh, float* __restrict__ dgr, int64_t lddg, float* __restrict__ dhh, int64_t lddhh,
+                                     int64_t rows, int H4) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H4) return;
   const int64_t row = i / H4;
   const int c = (int)(i - row * H4) * 4, H = H4 * 4;
-  const float4 d = *reinterpret_cast<const float4*>(dhn + row * H + c), zv = *reinterpret_cast<const float4*>(z + row * H + c);
-  const float4 t = *reinterpret_cast<const float4*>(cand + row * H + c), b = *reinterpret_cast<const float4*>(hh + row * ldhh + c);
-  *reinterpret_cast<float4*>(dgz + row * lddg + c) =
-      make_float4(d.x * (t.x - b.x) * zv.x * (1.f - zv.x), d.y * (t.y - b.y) * zv.y * (1.f - zv.y),
-                  d.z * (t.z - b.z) * zv.z * (1.f - zv.z), d.w * (t.w - b.w) * zv.w * (1.f - zv.w));
-  *reinterpret_cast<float4*>(dgc + row * lddg + c) =
-      make_float4(d.x * zv.x * (1.f - t.x * t.x), d.y * zv.y * (1.f - t.y * t.y), d.z * zv.z * (1.f - t.z * t.z),
-                  d.w * zv.w * (1.f - t.w * t.w));
-  *reinterpret_cast<float4*>(dhh + row * lddhh + c) =
-      make_float4(d.x * (1.f - zv.x), d.y * (1.f - zv.y), d.z * (1.f - zv.z), d.w * (1.f - zv.w));
+  const float4 d = *reinterpret_cast<const float4*>(drs + row * H + c), rv = *reinterpret_cast<const float4*>(r + row * H + c);
+  const float4 b = *reinterpret_cast<const float4*>(hh + row * ldhh + c);
+  float4* op = reinterpret_cast<float4*>(dhh + row * lddhh + c);
+  const float4 o = *op;
+  *reinterpret_cast<float4*>(dgr + row * lddg + c) =
+      make_float4(d.x * b.x * rv.x * (1.f - rv.x), d.y * b.y * rv.y * (1.f - rv.y), d.z * b.z * rv.z * (1.f - rv.z),
+                  d.w * b.w * rv.w * (1.f - rv.w));
+  *op = make_float4(o.x + d.x * rv.x, o.y + d.y * rv.y, o.z + d.z * rv.z, o.w + d.w * rv.w);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -466,38 +499,61 @@ int parts_for(int64_t rows) {
     else { CALL(16, false); }                                                \
   } while (0)
 
+static int ln_pair_fwd_impl(const float* hn, int64_t ldhn, const float* bz, const float* bbase, int64_t ldbase, float* cand,
+                           const float* gamma_o, const float* beta_o, const float* gamma_h, const float* beta_h,
+                           const float* ts, int64_t ldts, int32_t t_hi, float* s, int64_t lds, float* hhat, int64_t ldhh,
+                           float* mean_o, float* rstd_o, float* mean_h, float* rstd_h, float* decay, int64_t rows, int32_t cols,
+                           tagan_stream_t stream) {
+  if (!hn || !gamma_o || !beta_o || !s || !mean_o || !rstd_o || rows < 0 || cols <= 0) return TAGAN_E_INVALID;
+  if (hhat && (!gamma_h || !beta_h || !mean_h || !rstd_h)) return TAGAN_E_INVALID;
+  if (bz && (!bbase || !cand)) return TAGAN_E_INVALID;
+  if (ts && t_hi < 1) return TAGAN_E_INVALID;
+  if (cols > 512) return TAGAN_E_UNSUPPORTED;
+  if (rows == 0) return 0;
+  const bool vec = ldhn % 4 == 0 && lds % 4 == 0 && (!hhat || ldhh % 4 == 0) && al16(hn) && al16(s) && al16(hhat) &&
+                   al16(gamma_o) && al16(beta_o) && al16(gamma_h) && al16(beta_h) &&
+                   (!bz || (al16(bz) && al16(bbase) && al16(cand) && ldbase % 4 == 0));
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = ceil_div_i64(rows, RW);
+#define CALL(NV, VEC) ln_pair_fwd_kernel<NV, VEC><<<grid, RW * 32, 0, st>>>(hn, ldhn, bz, bbase, ldbase, cand, gamma_o, beta_o, gamma_h, \
+      beta_h, ts, ldts, t_hi, s, lds, hhat, ldhh, mean_o, rstd_o, mean_h, rstd_h, decay, rows, cols)
+  ROW_DISPATCH(vec, cols, CALL);
+#undef CALL
+  return tagan_launch_status();
+}
+
 TAGAN_API int tagan_ln_pair_fwd(const float* hn, int64_t ldhn, const float* gamma_o, const float* beta_o,
                                 const float* gamma_h, const float* beta_h, const float* ts, int64_t ldts, int32_t t_hi,
                                 float* s, int64_t lds, float* hhat, int64_t ldhh, float* mean_o, float* rstd_o,
                                 float* mean_h, float* rstd_h, float* decay, int64_t rows, int32_t cols,
                                 tagan_stream_t stream) {
-  if (!hn || !gamma_o || !beta_o || !s || !mean_o || !rstd_o || rows < 0 || cols <= 0) return TAGAN_E_INVALID;
-  if (hhat && (!gamma_h || !beta_h || !mean_h || !rstd_h)) return TAGAN_E_INVALID;
-  if (ts && t_hi < 1) return TAGAN_E_INVALID;
-  if (cols > 512) return TAGAN_E_UNSUPPORTED;
-  if (rows == 0) return 0;
-  const bool vec = ldhn % 4 == 0 && lds % 4 == 0 && (!hhat || ldhh % 4 == 0) && al16(hn) && al16(s) && al16(hhat) &&
-                   al16(gamma_o) && al16(beta_o) && al16(gamma_h) && al16(beta_h);
-  cudaStream_t st = as_stream(stream);
-  const unsigned grid = ceil_div_i64(rows, RW);
-#define CALL(NV, VEC) ln_pair_fwd_kernel<NV, VEC><<<grid, RW * 32, 0, st>>>(hn, ldhn, gamma_o, beta_o, gamma_h, beta_h, ts, ldts, \
-      t_hi, s, lds, hhat, ldhh, mean_o, rstd_o, mean_h, rstd_h, decay, rows, cols)
-  ROW_DISPATCH(vec, cols, CALL);
-#undef CALL
-  return tagan_launch_status();
+  return ln_pair_fwd_impl(hn, ldhn, nullptr, nullptr, 0, nullptr, gamma_o, beta_o, gamma_h, beta_h, ts, ldts, t_hi, s, lds, hhat,
+                          ldhh, mean_o, rstd_o, mean_h, rstd_h, decay, rows, cols, stream);
+}
+
+TAGAN_API int tagan_gru_blend_ln_fwd(const float* cand_pre, int64_t ldc, const float* z, const float* hhat_cur, int64_t ldcur,
+                                     float* cand, const float* gamma_o, const float* beta_o, const float* gamma_h,
+                                     const float* beta_h, const float* ts, int64_t ldts, int32_t t_hi, float* s, int64_t lds,
+                                     float* hhat_next, int64_t ldhh, float* mean_o, float* rstd_o, float* mean_h, float* rstd_h,
+                                     float* decay, int64_t rows, int32_t cols, tagan_stream_t stream) {
+  if (!z || !hhat_cur || !cand) return TAGAN_E_INVALID;
+  return ln_pair_fwd_impl(cand_pre, ldc, z, hhat_cur, ldcur, cand, gamma_o, beta_o, gamma_h, beta_h, ts, ldts, t_hi, s, lds,
+                          hhat_next, ldhh, mean_o, rstd_o, mean_h, rstd_h, decay, rows, cols, stream);
 }
 
 TAGAN_API size_t tagan_ln_pair_bwd_workspace_bytes(int64_t rows, int32_t cols) {
   return (size_t)parts_for(rows) * 4 * (size_t)cols * sizeof(float);
 }
 
-TAGAN_API int tagan_ln_pair_bwd(const float* ds_ext, int64_t ldds, const float* dhh, int64_t lddhh, const float* hn,
-                                int64_t ldhn, const float* gamma_o, const float* beta_o, const float* gamma_h,
-                                const float* mean_o, const float* rstd_o, const float* mean_h, const float* rstd_h,
-                                const float* decay, float* dhn, int64_t lddhn, float* daffine /*[4][cols]*/,
-                                int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t rows, int32_t cols,
-                                tagan_stream_t stream) {
-  if (!hn || !gamma_o || !beta_o || !mean_o || !rstd_o || !dhn || !daffine || rows < 0 || cols <= 0) return TAGAN_E_INVALID;
+static int ln_pair_bwd_impl(const float* ds_ext, int64_t ldds, const float* dhh, int64_t lddhh, const float* hn, int64_t ldhn,
+                           const float* bz, const float* bbase, int64_t ldbase, float* dgz, float* dgc, int64_t lddg,
+                           float* dbase, int64_t lddbase, const float* gamma_o, const float* beta_o, const float* gamma_h,
+                           const float* mean_o, const float* rstd_o, const float* mean_h, const float* rstd_h,
+                           const float* decay, float* dhn, int64_t lddhn, float* daffine, int32_t accumulate, void* workspace,
+                           size_t workspace_bytes, int64_t rows, int32_t cols, tagan_stream_t stream) {
+  if (!hn || !gamma_o || !beta_o || !mean_o || !rstd_o || !daffine || rows < 0 || cols <= 0) return TAGAN_E_INVALID;
+  if (!bz && !dhn) return TAGAN_E_INVALID;
+  if (bz && (!bbase || !dgz || !dgc || !dbase)) return TAGAN_E_INVALID;
   if (dhh && (!gamma_h || !mean_h || !rstd_h)) return TAGAN_E_INVALID;
   if (cols > 512) return TAGAN_E_UNSUPPORTED;
   if (!workspace || workspace_bytes < tagan_ln_pair_bwd_workspace_bytes(rows, cols)) return TAGAN_E_WORKSPACE;
@@ -507,16 +563,53 @@ TAGAN_API int tagan_ln_pair_bwd(const float* ds_ext, int64_t ldds, const float* 
   const int64_t rpb = (rows + parts - 1) / parts;
   float* part = static_cast<float*>(workspace);
   const bool vec = (!ds_ext || (ldds % 4 == 0 && al16(ds_ext))) && (!dhh || (lddhh % 4 == 0 && al16(dhh))) && ldhn % 4 == 0 &&
-                   lddhn % 4 == 0 && al16(hn) && al16(dhn) && al16(gamma_o) && al16(beta_o) && al16(gamma_h);
+                   (!dhn || (lddhn % 4 == 0 && al16(dhn))) && al16(hn) && al16(gamma_o) && al16(beta_o) && al16(gamma_h) &&
+                   (!bz || (al16(bz) && al16(bbase) && al16(dgz) && al16(dgc) && al16(dbase) && ldbase % 4 == 0 && lddg % 4 == 0 &&
+                            lddbase % 4 == 0));
   const size_t smem = (size_t)RW * 4 * cols * sizeof(float);
-#define CALL(NV, VEC) ln_pair_bwd_kernel<NV, VEC><<<parts, RW * 32, smem, st>>>(ds_ext, ldds, dhh, lddhh, hn, ldhn, gamma_o, beta_o, \
-      gamma_h, mean_o, rstd_o, mean_h, rstd_h, decay, dhn, lddhn, part, rows, cols, rpb)
+#define CALL(NV, VEC) ln_pair_bwd_kernel<NV, VEC><<<parts, RW * 32, smem, st>>>(ds_ext, ldds, dhh, lddhh, hn, ldhn, bz, bbase, ldbase, \
+      dgz, dgc, lddg, dbase, lddbase, gamma_o, beta_o, gamma_h, mean_o, rstd_o, mean_h, rstd_h, decay, dhn, lddhn, part, rows, cols, rpb)
   if (smem > 48 * 1024) {          // cols > 384 with four accumulators: opt in once per launch (cheap, idempotent)
     cudaFuncSetAttribute(ln_pair_bwd_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   ROW_DISPATCH(vec, cols, CALL);
 #undef CALL
   reduce_cols_kernel<<<(4 * cols + 31) / 32, 256, 0, st>>>(part, parts, 4 * cols, daffine, accumulate);
+  return tagan_launch_status();
+}
+
+TAGAN_API int tagan_ln_pair_bwd(const float* ds_ext, int64_t ldds, const float* dhh, int64_t lddhh, const float* hn,
+                                int64_t ldhn, const float* gamma_o, const float* beta_o, const float* gamma_h,
+                                const float* mean_o, const float* rstd_o, const float* mean_h, const float* rstd_h,
+                                const float* decay, float* dhn, int64_t lddhn, float* daffine /*[4][cols]*/,
+                                int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t rows, int32_t cols,
+                                tagan_stream_t stream) {
+  if (!dhn) return TAGAN_E_INVALID;
+  return ln_pair_bwd_impl(ds_ext, ldds, dhh, lddhh, hn, ldhn, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, gamma_o, beta_o,
+                          gamma_h, mean_o, rstd_o, mean_h, rstd_h, decay, dhn, lddhn, daffine, accumulate, workspace,
+                          workspace_bytes, rows, cols, stream);
+}
+
+TAGAN_API int tagan_gru_blend_ln_bwd(const float* ds_ext, int64_t ldds, const float* dhh_next, int64_t lddhh, const float* cand,
+                                     const float* z, const float* hhat_cur, int64_t ldcur, float* dgz, float* dgc, int64_t lddg,
+                                     float* dhh_cur, int64_t lddcur, const float* gamma_o, const float* beta_o,
+                                     const float* gamma_h, const float* mean_o, const float* rstd_o, const float* mean_h,
+                                     const float* rstd_h, const float* decay, float* daffine, int32_t accumulate, void* workspace,
+                                     size_t workspace_bytes, int64_t rows, int32_t cols, tagan_stream_t stream) {
+  if (!cand || !z || !hhat_cur) return TAGAN_E_INVALID;
+  return ln_pair_bwd_impl(ds_ext, ldds, dhh_next, lddhh, cand, cols, z, hhat_cur, ldcur, dgz, dgc, lddg, dhh_cur, lddcur, gamma_o,
+                          beta_o, gamma_h, mean_o, rstd_o, mean_h, rstd_h, decay, nullptr, 0, daffine, accumulate, workspace,
+                          workspace_bytes, rows, cols, stream);
+}
+
+TAGAN_API int tagan_gru_reset_bwd(const float* drs, const float* r, const float* hhat, int64_t ldhh, float* dgr, int64_t lddg,
+                                  float* dhh, int64_t lddhh, int64_t rows, int32_t H, tagan_stream_t stream) {
+  if (!drs || !r || !hhat || !dgr || !dhh || rows < 0 || H <= 0) return TAGAN_E_INVALID;
+  if (H % 4 || ldhh % 4 || lddg % 4 || lddhh % 4 || !al16(drs) || !al16(r) || !al16(hhat) || !al16(dgr) || !al16(dhh))
+    return TAGAN_E_UNSUPPORTED;
+  if (rows == 0) return 0;
+  gru_reset_bwd_kernel<<<ceil_div_i64(rows * (H / 4), 256), 256, 0, as_stream(stream)>>>(drs, r, hhat, ldhh, dgr, lddg, dhh, lddhh,
+                                                                                       rows, H / 4);
   return tagan_launch_status();
 }
 
@@ -612,18 +705,5 @@ TAGAN_API int tagan_mse_bwd(const float* x, int64_t n, const float* dloss, float
   if (!al16(x) || !al16(dx)) return TAGAN_E_UNSUPPORTED;
   const int64_t n4 = n / 4;
   scale_by_dev_scalar_kernel<<<ceil_div_i64(n4 > 0 ? n4 : 1, 256), 256, 0, as_stream(stream)>>>(x, dloss, 2.f / (float)n, dx, n4, n);
-  return tagan_launch_status();
-}
-
-TAGAN_API int tagan_gru_blend_bwd(const float* dhn, const float* z, const float* cand, const float* hhat, int64_t ldhh,
-                                  float* dgz, float* dgc, int64_t lddg, float* dhh, int64_t lddhh, int64_t rows, int32_t H,
-                                  tagan_stream_t stream) {
-  if (!dhn || !z || !cand || !hhat || !dgz || !dgc || !dhh || rows < 0 || H <= 0) return TAGAN_E_INVALID;
-  if (H % 4 || ldhh % 4 || lddg % 4 || lddhh % 4 || !al16(dhn) || !al16(z) || !al16(cand) || !al16(hhat) || !al16(dgz) ||
-      !al16(dgc) || !al16(dhh))
-    return TAGAN_E_UNSUPPORTED;
-  if (rows == 0) return 0;
-  gru_blend_bwd_kernel<<<ceil_div_i64(rows * (H / 4), 256), 256, 0, as_stream(stream)>>>(dhn, z, cand, hhat, ldhh, dgz, dgc, lddg,
-                                                                                       dhh, lddhh, rows, H / 4);
   return tagan_launch_status();
 }

@@ -18,7 +18,8 @@ size_t tagan_gemm_tma_colsum_bytes(int64_t M, int64_t N, int64_t K);
 int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                    int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
                    void* workspace, size_t workspace_bytes, cudaStream_t st, float* colsum_a,
-                   const float* A2 = nullptr, int64_t lda2 = 0, int64_t K1 = 0, const tagan_epilogue* epi = nullptr);
+                   const float* A2 = nullptr, int64_t lda2 = 0, int64_t K1 = 0, const tagan_epilogue* epi = nullptr,
+                   int32_t epi_fast = 0);
 
 TAGAN_API size_t tagan_gemm_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k) {
   if (op < 0 || op > 2 || m < 0 || n < 0 || k < 0) return 0;
@@ -92,6 +93,8 @@ TAGAN_API int tagan_gemm_fused(int32_t op, int64_t m, int64_t n, int64_t k, cons
                                const struct tagan_epilogue* epi, int32_t precision, void* workspace, size_t workspace_bytes,
                                tagan_stream_t stream) {
   if (op < 0 || op > 1 || m < 0 || n <= 0 || k <= 0 || !A || !B || !epi || !epi->out0) return TAGAN_E_INVALID;
+  const int32_t epi_fast = precision & 8;                  // +8: MUFU-based sigmoid / tanh in the epilogue
+  precision &= 7;
   if (precision < 1 || precision > 3) return TAGAN_E_INVALID;
   if (m == 0) return 0;
   const tagan_epilogue& e = *epi;
@@ -120,5 +123,5 @@ TAGAN_API int tagan_gemm_fused(int32_t op, int64_t m, int64_t n, int64_t k, cons
   if (A2 && ((reinterpret_cast<uintptr_t>(A2) & 15) || lda2 % 4)) return TAGAN_E_UNSUPPORTED;
   const int passes = (precision & 3) == 1 ? 3 : ((precision & 3) == 3 ? 4 : 1);
   return tagan_gemm_tma(op, m, n, k, A, lda, B, ldb, bias, e.out0, e.ld_out0, 0, passes, workspace, workspace_bytes,
-                        as_stream(stream), nullptr, A2, lda2, k1, epi);
+                        as_stream(stream), nullptr, A2, lda2, k1, epi, epi_fast);
 }

@@ -154,7 +154,17 @@ struct Params {
 // row-contiguous layout: lane holds rows 4*i + (lane >> 3), i = 0..7, columns 4*(lane & 7)..+3 of the chunk, so
 // every global access below is a 128-byte row segment per 8 lanes.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_e(float x) { return 1.f / (1.f + expf(-x)); }
+// FAST: MUFU-based exp / reciprocal (relative error ~1e-6, far inside the 1e-5 parity band): the four epilogue warps
+// are the only threads that see the accumulator, so their instruction count bounds the whole GEMM
+template <bool FAST> __device__ __forceinline__ float sigmoid_e(float x) {
+  return FAST ? __fdividef(1.f, 1.f + __expf(-x)) : 1.f / (1.f + expf(-x));
+}
+template <bool FAST> __device__ __forceinline__ float tanh_e(float x) {
+  if (!FAST) return tanhf(x);
+  const float a = fminf(fabsf(x), 15.f);                 // tanh(|x|) = 1 - 2 / (1 + e^{2|x|}), odd extension
+  const float t = 1.f - __fdividef(2.f, 1.f + __expf(2.f * a));
+  return copysignf(t, x);
+}
 __device__ __forceinline__ float4 ld4g(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4g(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
@@ -185,6 +195,7 @@ __device__ __forceinline__ void epi_load_chunk(uint32_t taddr, uint32_t stg, int
 // One 128x128 tile through a fused epilogue; arrives on the accumulator's "empty" barrier as soon as the last
 // tcgen05.ld of the tile has completed (before the second LayerNorm phase), so the MMA warp never waits on the
 // normalisation pass.
+template <bool FAST>
 __device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int lane, int acc, int mt, int64_t n0,
                                                uint32_t epi_u32, uint64_t* tmem_empty_bar) {
   const tagan_epilogue& e = p.epi;
@@ -317,8 +328,8 @@ __device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int la
           const int64_t grow = row0 + 4 * i;
           if (!(cok && grow < p.M)) continue;
           float4 s;
-          s.x = sigmoid_e(v[i].x + b4.x); s.y = sigmoid_e(v[i].y + b4.y);
-          s.z = sigmoid_e(v[i].z + b4.z); s.w = sigmoid_e(v[i].w + b4.w);
+          s.x = sigmoid_e<FAST>(v[i].x + b4.x); s.y = sigmoid_e<FAST>(v[i].y + b4.y);
+          s.z = sigmoid_e<FAST>(v[i].z + b4.z); s.w = sigmoid_e<FAST>(v[i].w + b4.w);
           if (rpart) {
             st4g(e.out0 + grow * e.ld_out0 + c0, s);
             st4g(e.out1 + grow * e.ld_out1 + c0, make_float4(s.x * a0[q].x, s.y * a0[q].y, s.z * a0[q].z, s.w * a0[q].w));
@@ -339,7 +350,8 @@ __device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int la
           const int64_t grow = row0 + 4 * i;
           if (!(cok && grow < p.M)) continue;
           float4 t, o;
-          t.x = tanhf(v[i].x + b4.x); t.y = tanhf(v[i].y + b4.y); t.z = tanhf(v[i].z + b4.z); t.w = tanhf(v[i].w + b4.w);
+          t.x = tanh_e<FAST>(v[i].x + b4.x); t.y = tanh_e<FAST>(v[i].y + b4.y);
+          t.z = tanh_e<FAST>(v[i].z + b4.z); t.w = tanh_e<FAST>(v[i].w + b4.w);
           o.x = (1.f - a0[q].x) * a1[q].x + a0[q].x * t.x;
           o.y = (1.f - a0[q].y) * a1[q].y + a0[q].y * t.y;
           o.z = (1.f - a0[q].z) * a1[q].z + a0[q].z * t.z;
@@ -594,7 +606,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (p.fused) {                                       // warp-uniform
-        epilogue_fused(p, warp, lane, acc, mt, n0, epi_u32, &tmem_empty[acc]);
+        if (p.fused == 2) epilogue_fused<true>(p, warp, lane, acc, mt, n0, epi_u32, &tmem_empty[acc]);
+        else epilogue_fused<false>(p, warp, lane, acc, mt, n0, epi_u32, &tmem_empty[acc]);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         continue;
       }
@@ -823,7 +836,7 @@ size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t 
 int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                    int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
                    void* workspace, size_t workspace_bytes, cudaStream_t st, float* colsum_a /* TN only, [M] or null */,
-                   const float* A2, int64_t lda2, int64_t K1, const tagan_epilogue* epi) {
+                   const float* A2, int64_t lda2, int64_t K1, const tagan_epilogue* epi, int32_t epi_fast) {
   // the opt-in to > 48 KB of dynamic shared memory is per device: remember it per device ordinal
   static bool attr_set[64] = {};
   int dev = 0;
@@ -841,7 +854,7 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   if (epi != nullptr) {
     if (op == 2 || pl.splits != 1 || colsum_a != nullptr || accumulate) return TAGAN_E_UNSUPPORTED;
     if (epi->mode == TAGAN_EPI_RES_LN && epi->gamma != nullptr && pl.tiles_n != 1) return TAGAN_E_UNSUPPORTED;
-    p.fused = 1;
+    p.fused = epi_fast ? 2 : 1;
     p.epi = *epi;
   }
   if (A2 != nullptr) {

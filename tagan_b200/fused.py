@@ -28,6 +28,12 @@ from .gru import _ln_bwd, _ln_fwd, _off
 from .ops import CALLS, _ptr, _stream, _timed, gemm, gemm_tn_colsum, workspace
 
 FUSED_GEMM = True          # GEMM epilogue fusion (tests flip it to compare with the unfused composition)
+EPI_FAST_MATH = False      # sigmoid / tanh of the GEMM epilogues through MUFU exp / reciprocal (rel. error ~1e-6)
+# output_proj + residual + LayerNorm as a GEMM epilogue.  Correct (tests/test_gpu_fused.py) but OFF by default: measured on
+# B200 (profiles/r02_fused_gemm_micro.jsonl) the 1.6M x 128 x 128 projection takes 1.56 ms with the epilogue against
+# 0.83 ms for GEMM + LayerNorm kernel -- the four epilogue warps keep only ~8 KB of residual loads in flight per SM
+# (ncu: long-scoreboard stalls 16.8 vs 3.8 per issue), far below what HBM latency needs.
+FUSED_RES_LN = False
 
 _F32 = torch.float32
 
@@ -67,7 +73,8 @@ def gemm_fused(op, m, n, k, a, lda, a2, lda2, k1, b, ldb, bias, epi, dev):
     ws = workspace(nbytes, dev) if nbytes else None
     with _timed("gemm", 4 * (m * k + n * k + m * n * _EPI_STREAMS[epi.mode])):
         rc = lib.tagan_gemm_fused(op, m, n, k, _ptr(a), lda, _ptr(a2), lda2, k1, _ptr(b), ldb, _ptr(bias), C.byref(epi),
-                                  ops.GEMM_PRECISION, _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+                                  ops.GEMM_PRECISION | (8 if EPI_FAST_MATH else 0), _ptr(ws),
+                                  ws.numel() if ws is not None else 0, _stream())
     _lib.check(rc, "tagan_gemm_fused")
     CALLS["n"] += 2
 
@@ -83,7 +90,7 @@ def linear_res_ln(x2, w, bias, res, gamma, beta, need_sum=True):
     y = _e(m, n, dev=dev)
     mean, rstd = _e(m, dev=dev), _e(m, dev=dev)
     xsum = _e(m, n, dev=dev) if need_sum else None
-    if (_use_fused_gemm() and n <= 128 and n % 4 == 0 and ldx % 4 == 0 and w.stride(0) % 4 == 0 and m > 0
+    if (_use_fused_gemm() and FUSED_RES_LN and n <= 128 and n % 4 == 0 and ldx % 4 == 0 and w.stride(0) % 4 == 0 and m > 0
             and _al(x2, w, bias, res, gamma, beta)):
         epi = _epi(_lib.EPI_RES_LN, in0=res, ld_in0=n, out0=y, ld_out0=n, out1=xsum, ld_out1=n, gamma=gamma, beta=beta,
                    mean=mean, rstd=rstd)
@@ -253,36 +260,35 @@ class _EvolutionFn(torch.autograd.Function):
         w_c = w_c.contiguous()
         kk = din + hd
         hhat = _e(t_steps, n, hd, dev=dev)
-        r, z, rs, cand, hn, s = (_e(t_steps, n, hd, dev=dev) for _ in range(6))
+        r, z, rs, cand, s = (_e(t_steps, n, hd, dev=dev) for _ in range(5))
         mean_o, rstd_o, mean_h, rstd_h = (_e(t_steps, n, dev=dev) for _ in range(4))
         ts_c = ts.contiguous().float() if ts is not None else None
         decay = _e(t_steps, n, dev=dev) if ts_c is not None else None
+        g_rz, g_c = _e(n, 2 * hd, dev=dev), _e(n, hd, dev=dev)                     # per-step pre-activations (scratch)
         nh = n * hd
         hhat[0].zero_()                                                           # h is None -> zeros, no LayerNorm (:503-504)
         for t in range(t_steps):
             x_t, hh_t = _off(xhat, t * n * din), _off(hhat, t * nh)
-            # r, z = sigmoid(W_rz [x^ | h^] + b); rs = r * h^                     (:531-535)
-            epi = _epi(_lib.EPI_GATES, split=hd, in0=hh_t, ld_in0=hd, out0=_off(r, t * nh), ld_out0=hd,
-                       out1=_off(rs, t * nh), ld_out1=hd, out2=_off(z, t * nh), ld_out2=hd)
-            gemm_fused(0, n, 2 * hd, kk, x_t, din, hh_t, hd, din, w_rz, kk, b_rz, epi, dev)
-            # cand = tanh(W_c [x^ | rs] + b); hn = (1 - z) h^ + z cand            (:538-542)
-            epi = _epi(_lib.EPI_BLEND, in0=_off(z, t * nh), ld_in0=hd, in1=hh_t, ld_in1=hd, out0=_off(cand, t * nh), ld_out0=hd,
-                       out1=_off(hn, t * nh), ld_out1=hd)
-            gemm_fused(0, n, hd, kk, x_t, din, _off(rs, t * nh), hd, din, w_c, kk, b_c, epi, dev)
-            # s_t = LN_out(hn) (:545-546); h^_{t+1} = LN_h(s_t) * exp(-clamp(dt, 0, 10)) (:505-514)
+            # [r_pre | z_pre] = [x^ | h^] . W_rz^T + b: the concatenation of :531 as a two-source A operand
+            gemm_fused(0, n, 2 * hd, kk, x_t, din, hh_t, hd, din, w_rz, kk, b_rz, _epi(_lib.EPI_STORE, out0=g_rz, ld_out0=2 * hd), dev)
+            _lib.check(lib.tagan_gates_fwd(_ptr(g_rz), 2 * hd, hh_t, hd, _off(r, t * nh), _off(z, t * nh), _off(rs, t * nh), hd,
+                                           n, hd, _stream()), "tagan_gates_fwd")                       # :531-535
+            gemm_fused(0, n, hd, kk, x_t, din, _off(rs, t * nh), hd, din, w_c, kk, b_c, _epi(_lib.EPI_STORE, out0=g_c, ld_out0=hd), dev)
+            # cand = tanh(.); hn = (1-z) h^ + z cand (:538-542); s_t = LN_out(hn) (:545-546);
+            # h^_{t+1} = LN_h(s_t) * exp(-clamp(dt, 0, 10)) (:505-514) -- one pass, hn never stored
             last = t == t_steps - 1
-            rc = lib.tagan_ln_pair_fwd(_off(hn, t * nh), hd, _ptr(lno_w), _ptr(lno_b), _ptr(lnh_w), _ptr(lnh_b),
-                                       _ptr(ts_c) if not last else None, ts_c.stride(0) if ts_c is not None else 0, t + 1,
-                                       _off(s, t * nh), hd, None if last else _off(hhat, (t + 1) * nh), hd,
-                                       _off(mean_o, t * n), _off(rstd_o, t * n),
-                                       None if last else _off(mean_h, (t + 1) * n), None if last else _off(rstd_h, (t + 1) * n),
-                                       None if (last or decay is None) else _off(decay, (t + 1) * n), n, hd, _stream())
-            _lib.check(rc, "tagan_ln_pair_fwd")
-            CALLS["n"] += 1
+            rc = lib.tagan_gru_blend_ln_fwd(_ptr(g_c), hd, _off(z, t * nh), hh_t, hd, _off(cand, t * nh), _ptr(lno_w), _ptr(lno_b),
+                                            _ptr(lnh_w), _ptr(lnh_b), _ptr(ts_c) if not last else None,
+                                            ts_c.stride(0) if ts_c is not None else 0, t + 1, _off(s, t * nh), hd,
+                                            None if last else _off(hhat, (t + 1) * nh), hd, _off(mean_o, t * n), _off(rstd_o, t * n),
+                                            None if last else _off(mean_h, (t + 1) * n), None if last else _off(rstd_h, (t + 1) * n),
+                                            None if (last or decay is None) else _off(decay, (t + 1) * n), n, hd, _stream())
+            _lib.check(rc, "tagan_gru_blend_ln_fwd")
+            CALLS["n"] += 2
         res = xrows if (residual and din == w_o.shape[0]) else None
         need = any(ctx.needs_input_grad)
         e, xsum, mean_e, rstd_e = linear_res_ln(s.view(rows, hd), w_o, b_o, res, ln_w, ln_b, need_sum=need)   # :738-753
-        ctx.save_for_backward(xrows, xhat, mean_x, rstd_x, hhat, r, z, rs, cand, hn, s, mean_o, rstd_o, mean_h, rstd_h, decay,
+        ctx.save_for_backward(xrows, xhat, mean_x, rstd_x, hhat, r, z, rs, cand, s, mean_o, rstd_o, mean_h, rstd_h, decay,
                               lnx_w, lnh_w, lno_w, lno_b, w_rz, w_c, w_o, ln_w, xsum, mean_e, rstd_e)
         ctx.dims, ctx.has_res = (t_steps, n, din, hd), res is not None
         return e.view(t_steps, n, w_o.shape[0])
@@ -290,7 +296,7 @@ class _EvolutionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, de):
         lib = _lib.load()
-        (xrows, xhat, mean_x, rstd_x, hhat, r, z, rs, cand, hn, s, mean_o, rstd_o, mean_h, rstd_h, decay, lnx_w, lnh_w,
+        (xrows, xhat, mean_x, rstd_x, hhat, r, z, rs, cand, s, mean_o, rstd_o, mean_h, rstd_h, decay, lnx_w, lnh_w,
          lno_w, lno_b, w_rz, w_c, w_o, ln_w, xsum, mean_e, rstd_e) = ctx.saved_tensors
         t_steps, n, din, hd = ctx.dims
         rows, nh, kk = t_steps * n, n * hd, din + hd
@@ -304,34 +310,35 @@ class _EvolutionFn(torch.autograd.Function):
         ds = _e(rows, hd, dev=dev)                                                # external gradient of every s_t
         gemm(1, rows, hd, hout, d_o, hout, w_o, hd, None, ds, hd)
         dg = _e(rows, 3 * hd, dev=dev)                                            # [d r_pre | d z_pre | d cand_pre]
-        dhn = _e(n, hd, dev=dev)
-        dhh = _e(n, hd, dev=dev)                                                  # gradient of h^ of the step being visited
+        dhh_a, dhh_b = _e(n, hd, dev=dev), _e(n, hd, dev=dev)                     # gradient of h^: next step's (in) / this step's (out)
+        drs = _e(n, hd, dev=dev)
         daff = torch.zeros(4, hd, dtype=_F32, device=dev)                         # d gamma_o, d beta_o, d gamma_h, d beta_h
         ws_pair = workspace(lib.tagan_ln_pair_bwd_workspace_bytes(n, hd), dev)
         w_c_h = C.c_void_p(w_c.data_ptr() + din * 4)                              # W_c[:, in:]  ([H, H], ld in+H)
         w_rz_h = C.c_void_p(w_rz.data_ptr() + din * 4)                            # W_rz[:, in:] ([2H, H], ld in+H)
         for t in range(t_steps - 1, -1, -1):
             last = t == t_steps - 1
-            rc = lib.tagan_ln_pair_bwd(_off(ds, t * nh), hd, None if last else _ptr(dhh), hd, _off(hn, t * nh), hd,
-                                       _ptr(lno_w), _ptr(lno_b), _ptr(lnh_w), _off(mean_o, t * n), _off(rstd_o, t * n),
-                                       None if last else _off(mean_h, (t + 1) * n), None if last else _off(rstd_h, (t + 1) * n),
-                                       None if (last or decay is None) else _off(decay, (t + 1) * n), _ptr(dhn), hd,
-                                       _ptr(daff), 1, _ptr(ws_pair), ws_pair.numel(), n, hd, _stream())
-            _lib.check(rc, "tagan_ln_pair_bwd")
             dg_t = t * n * 3 * hd
-            rc = lib.tagan_gru_blend_bwd(_ptr(dhn), _off(z, t * nh), _off(cand, t * nh), _off(hhat, t * nh), hd,
-                                         _off(dg, dg_t + hd), _off(dg, dg_t + 2 * hd), 3 * hd, _ptr(dhh), hd, n, hd, _stream())
-            _lib.check(rc, "tagan_gru_blend_bwd")
-            CALLS["n"] += 3
+            # LN_h' of step t+1, LN_out' and the blend of step t in one pass: d z_pre, d cand_pre into their slices, d h^_t
+            rc = lib.tagan_gru_blend_ln_bwd(_off(ds, t * nh), hd, None if last else _ptr(dhh_a), hd, _off(cand, t * nh),
+                                            _off(z, t * nh), _off(hhat, t * nh), hd, _off(dg, dg_t + hd), _off(dg, dg_t + 2 * hd),
+                                            3 * hd, _ptr(dhh_b), hd, _ptr(lno_w), _ptr(lno_b), _ptr(lnh_w), _off(mean_o, t * n),
+                                            _off(rstd_o, t * n), None if last else _off(mean_h, (t + 1) * n),
+                                            None if last else _off(rstd_h, (t + 1) * n),
+                                            None if (last or decay is None) else _off(decay, (t + 1) * n), _ptr(daff), 1,
+                                            _ptr(ws_pair), ws_pair.numel(), n, hd, _stream())
+            _lib.check(rc, "tagan_gru_blend_ln_bwd")
+            CALLS["n"] += 2
             if t > 0:
-                # d(rs) = d cand_pre . W_c[:, in:] consumed in the epilogue: d r_pre = d(rs) h^ r(1-r); dhh += d(rs) r
-                epi = _epi(_lib.EPI_GATES_BWD, in0=_off(r, t * nh), ld_in0=hd, in1=_off(hhat, t * nh), ld_in1=hd,
-                           out0=_off(dg, dg_t), ld_out0=3 * hd, out1=dhh, ld_out1=hd)
-                gemm_fused(1, n, hd, hd, _off(dg, dg_t + 2 * hd), 3 * hd, None, 0, 0, w_c_h, kk, None, epi, dev)
-                # dhh += [d r_pre | d z_pre] . W_rz[:, in:]
-                gemm(1, n, hd, 2 * hd, _off(dg, dg_t), 3 * hd, w_rz_h, kk, None, dhh, hd, accumulate=True)
+                # d(rs) = d cand_pre . W_c[:, in:];  d r_pre = d(rs) h^ r(1-r);  dhh += d(rs) r;  dhh += [d r_pre | d z_pre] . W_rz[:, in:]
+                gemm(1, n, hd, hd, _off(dg, dg_t + 2 * hd), 3 * hd, w_c_h, kk, None, drs, hd)
+                _lib.check(lib.tagan_gru_reset_bwd(_ptr(drs), _off(r, t * nh), _off(hhat, t * nh), hd, _off(dg, dg_t), 3 * hd,
+                                                   _ptr(dhh_b), hd, n, hd, _stream()), "tagan_gru_reset_bwd")
+                CALLS["n"] += 1
+                gemm(1, n, hd, 2 * hd, _off(dg, dg_t), 3 * hd, w_rz_h, kk, None, dhh_b, hd, accumulate=True)
             else:
                 dg.view(t_steps, n, 3 * hd)[0, :, :hd].zero_()                    # h^_0 = 0: no gradient through r
+            dhh_a, dhh_b = dhh_b, dhh_a
         # weight gradients over all T*N rows; step 0 contributes zeros through h^ = r*h^ = 0
         w_x = torch.cat([w_rz[:, :din], w_c[:, :din]], 0).contiguous()             # [3H, in]
         dxhat = _e(rows, din, dev=dev)

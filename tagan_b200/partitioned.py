@@ -235,3 +235,107 @@ def geometric_stage_part(layer, xs_loc, csrs, comm, n_src: int):
         outs.append(_finish(layer, ctxv, xs_loc[t]))
         qkv[t] = kv[t] = None
     return outs
+
+
+# ------------------------------------------------------------------------------------------
+# Snapshot-parallel geometric stage (T % world == 0): no per-snapshot halo at all
+# ------------------------------------------------------------------------------------------
+class AllToAllComm:
+    """The one exchange of the snapshot-parallel mode: equal blocks over a torch.distributed group (NCCL over
+    NVLink; gloo on CPU for the host-logic tests).  ``world == 1`` is the identity."""
+
+    def __init__(self, world: int, group=None):
+        self.world, self.group = world, group
+
+    def all_to_all(self, send: torch.Tensor) -> torch.Tensor:
+        """send ``[world, ...]``: block r goes to rank r; returns ``[world, ...]`` with block s received from rank s."""
+        if self.world == 1:
+            return send
+        send = send.contiguous()
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv
+
+
+class _NodeToSnapshotFn(torch.autograd.Function):
+    """``[T, n_loc, H]`` (this rank's nodes, every snapshot) -> ``[T/world, N, H]`` (every node, this rank's snapshots).
+    Snapshot t belongs to rank t // (T/world), so the send buffer is the input itself; backward is the inverse."""
+
+    @staticmethod
+    def forward(ctx, x, comm: AllToAllComm):
+        t, n_loc, h = x.shape
+        w = comm.world
+        t_loc = t // w
+        recv = comm.all_to_all(x.contiguous().view(w, t_loc, n_loc, h))          # [src rank, t_loc, n_loc, H]
+        ctx.comm, ctx.shape = comm, (t, n_loc, h)
+        return recv.permute(1, 0, 2, 3).reshape(t_loc, w * n_loc, h)              # node order = rank order (contiguous ranges)
+
+    @staticmethod
+    def backward(ctx, d):
+        t, n_loc, h = ctx.shape
+        w = ctx.comm.world
+        send = d.reshape(t // w, w, n_loc, h).permute(1, 0, 2, 3).contiguous()     # [dst rank, t_loc, n_loc, H]
+        return ctx.comm.all_to_all(send).view(t, n_loc, h), None
+
+
+class _SnapshotToNodeFn(torch.autograd.Function):
+    """Inverse of ``_NodeToSnapshotFn``: ``[T/world, N, H]`` -> ``[T, n_loc, H]``."""
+
+    @staticmethod
+    def forward(ctx, y, comm: AllToAllComm):
+        t_loc, n, h = y.shape
+        w = comm.world
+        n_loc = n // w
+        send = y.reshape(t_loc, w, n_loc, h).permute(1, 0, 2, 3).contiguous()
+        ctx.comm, ctx.shape = comm, (t_loc, n, h)
+        return comm.all_to_all(send).view(w * t_loc, n_loc, h)
+
+    @staticmethod
+    def backward(ctx, d):
+        t_loc, n, h = ctx.shape
+        w = ctx.comm.world
+        recv = ctx.comm.all_to_all(d.contiguous().view(w, t_loc, n // w, h))
+        return recv.permute(1, 0, 2, 3).reshape(t_loc, n, h), None
+
+
+def node_to_snapshot(x, comm):
+    return _NodeToSnapshotFn.apply(x, comm)
+
+
+def snapshot_to_node(y, comm):
+    return _SnapshotToNodeFn.apply(y, comm)
+
+
+def snapshot_parallel_supported(t_steps: int, num_nodes: int, world: int) -> bool:
+    return world >= 1 and t_steps % world == 0 and num_nodes % world == 0
+
+
+def forward_snapshot_parallel(layer, x_loc: torch.Tensor, my_edge_indices, part: NodePartition, rank: int, comm: AllToAllComm,
+                              time_stamps=None, bank=None) -> torch.Tensor:
+    """The whole TAGAN layer on ONE large graph over ``world`` GPUs without a per-snapshot halo (config 4).
+
+    The geometric stage has no dependency across snapshots, the temporal stages none across nodes.  So:
+
+      x_loc [T, n_loc, H]  --all-to-all-->  [T/world, N, H]: this rank runs the UNPARTITIONED geometric layer (LN1, QKV,
+      kernel (a) over the full CSR, output_proj, LN2) on its T/world snapshots  --all-to-all-->  [T, n_loc, H]
+      -> GRU scan, skip connection, temporal attention, memory bank on this rank's nodes (purely local).
+
+    One exchange of ``(world-1)/world * T * n_loc * H`` floats each way (1.75 GB per rank at config 4 on 8 GPUs) replaces
+    the 2 * T all-gathers / reduce-scatters of the whole ``[N, 2H]`` K|V matrix of the halo path (57 GB per rank), and
+    the geometric kernels are exactly the single-GPU ones, so the forward is bit-identical to the unpartitioned layer.
+    ``my_edge_indices``: the GLOBAL edge lists of this rank's snapshots ``rank*T/world ... (rank+1)*T/world - 1``.
+    Weights are replicated; every rank holds a PARTIAL weight gradient (its snapshots / its nodes): all-reduce(sum)."""
+    t_steps, n_loc, _ = x_loc.shape
+    if not snapshot_parallel_supported(t_steps, part.num_nodes, comm.world):
+        raise ValueError("snapshot-parallel mode needs T % world == 0 and N % world == 0 (use forward_node_partitioned)")
+    assert len(my_edge_indices) == t_steps // comm.world
+    x_snap = node_to_snapshot(x_loc, comm)                                           # [T/world, N, H]
+    geo_snap = layer.geometric.forward_seq(x_snap, my_edge_indices)                  # single-GPU geometric layer
+    geo = snapshot_to_node(geo_snap, comm)                                           # [T, n_loc, H]
+    prop = layer.propagation.forward_core(geo, time_stamps)
+    if bank is not None:
+        ids = torch.arange(n_loc, dtype=torch.int32, device=prop.device)             # bank slots are local row ids
+        for t in range(t_steps):
+            bank.get_states(ids)
+            bank.update(ids, prop[t].detach(), t)
+    return layer.temporal_attention(prop, time_stamps=time_stamps, time_major=True)

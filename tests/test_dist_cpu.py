@@ -71,3 +71,39 @@ def test_node_partition_arithmetic():
         for node in {0, n // 2, n - 1}:
             lo, hi = part.bounds(part.owner(node))
             assert lo <= node < hi
+
+
+def _a2a_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tagan_b200 import partitioned
+    t, n, h = 2 * world, 3 * world, 4
+    n_loc, t_loc = n // world, t // world
+    # global tensor G[t, node, c] = 1000 t + 10 node + c; every rank holds its node slice
+    full = (1000.0 * torch.arange(t).view(t, 1, 1) + 10.0 * torch.arange(n).view(1, n, 1) + torch.arange(h).view(1, 1, h))
+    x_loc = full[:, rank * n_loc:(rank + 1) * n_loc].clone().requires_grad_(True)
+    comm = partitioned.AllToAllComm(world)
+    snap = partitioned.node_to_snapshot(x_loc, comm)                   # [t_loc, n, h]: every node, my snapshots
+    ok = torch.equal(snap.detach(), full[rank * t_loc:(rank + 1) * t_loc])
+    back = partitioned.snapshot_to_node(snap * 2.0, comm)              # [t, n_loc, h]
+    ok = ok and torch.equal(back.detach(), 2.0 * full[:, rank * n_loc:(rank + 1) * n_loc])
+    wgt = torch.arange(t * n_loc * h, dtype=torch.float32).view(t, n_loc, h) + rank
+    (back * wgt).sum().backward()                                      # gradient returns through both exchanges
+    ok = ok and torch.equal(x_loc.grad, 2.0 * wgt)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_snapshot_parallel_all_to_all_world2_gloo():
+    """node-partitioned <-> snapshot-partitioned exchange of tagan_b200.partitioned (forward values and the gradient
+    path through both all-to-alls) on two gloo ranks."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

@@ -281,9 +281,19 @@ def test_geo_attention_hub_rows_and_columns(dev, metric):
         torch.testing.assert_close(p.grad.cpu(), gref, **tol, msg=lambda m, k=k: f"d{k}: {m}")
     # deterministic
     xd2 = x.to(dev).requires_grad_(True)
-    out2 = layer(xd2, ei.to(dev))
+    out2, _ = layer(xd2, ei.to(dev), None, return_attention_weights=True)
     (out2 * wout.to(dev)).sum().backward()
     assert torch.equal(out2, out) and torch.equal(xd2.grad, xd.grad)
+    # the stage-fused path (no attention weights requested) on the same hubs: same numbers, and deterministic too
+    runs = []
+    for _ in range(2):
+        xd3 = x.to(dev).requires_grad_(True)
+        out3 = layer(xd3, ei.to(dev))
+        (out3 * wout.to(dev)).sum().backward()
+        runs.append((out3.detach(), xd3.grad))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    _close(runs[0][0].cpu(), ref.detach())
+    _close(runs[0][1].cpu(), xr.grad)
 
 
 def test_geo_attention_full_size_properties(dev):

@@ -176,3 +176,30 @@ def test_forward_node_partitioned_world1_matches_layer():
         if k in gref:
             torch.testing.assert_close(p.grad, gref[k], rtol=1e-4, atol=1e-4 * max(1.0, float(gref[k].abs().max())),
                                        msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_snapshot_parallel_world1_matches_layer():
+    """forward_snapshot_parallel with one rank (identity exchanges) == TAGANLayer.forward bit for bit, same gradients."""
+    import tagan_b200
+    from tagan_b200 import partitioned
+    from tagan_b200.dist import NodePartition
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    n, e, hdim, heads, t_steps = 384, 4000, 64, 4, 4
+    layer = tagan_b200.TAGANLayer(hdim, heads, "euclidean").to(dev)
+    xs = torch.randn(t_steps, n, hdim, device=dev)
+    eis = [torch.randint(0, n, (2, e), device=dev) for _ in range(t_steps)]
+    ts = torch.arange(t_steps, dtype=torch.float32, device=dev).expand(n, t_steps)
+    wout = torch.randn(n, t_steps, hdim, device=dev)
+    ref = layer(list(xs.unbind(0)), eis, ts)
+    (ref * wout).sum().backward()
+    gref = {k: p.grad.clone() for k, p in layer.named_parameters() if p.grad is not None}
+    layer.zero_grad(set_to_none=True)
+    x_in = xs.clone().requires_grad_(True)
+    out = partitioned.forward_snapshot_parallel(layer, x_in, eis, NodePartition(n, 1), 0, partitioned.AllToAllComm(1), ts)
+    (out * wout).sum().backward()
+    assert torch.equal(out, ref)
+    assert x_in.grad is not None and bool(torch.isfinite(x_in.grad).all())
+    for k, p in layer.named_parameters():
+        if k in gref:
+            assert torch.equal(p.grad, gref[k]), k
