@@ -1,0 +1,133 @@
+"""Round-2 parity additions: (1) a config-2-shaped power-law snapshot against the reference's DENSE module
+(golden produced by oracle/make_golden_r02.py), (2) full-size comparisons against the CPU oracle -- one config-3 snapshot
+of the geometric layer (100k nodes, 2M edges) and one 100k x 16 temporal-attention call -- and (3) per-node timestamps
+against the reference goldens.  Outputs at the literal rtol 1e-4 / atol 1e-5."""
+import pytest
+import torch
+
+from oracle import restate as R
+from parity_util import close as pclose
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_geo_power_law_vs_dense_reference_golden(dev, golden):
+    """N = 10 000 nodes / ~200k power-law edges (hub rows of ~1000 entries) through the dense reference (sdp), and a
+    1 200-node power-law snapshot with the default euclidean metric: outputs, dx and every parameter gradient."""
+    import tagan_b200
+    from oracle.make_golden_r02 import powerlaw_inputs
+    for c in golden("geo_c2_powerlaw.pt"):
+        x, ei, wout = powerlaw_inputs(c["n"], c["e"], c["hidden"], c["seed"])
+        assert float(x.double().sum()) == c["x_checksum"] and int(ei.sum()) == c["ei_checksum"]
+        layer = tagan_b200.TAGANGraphAttention(c["hidden"], c["heads"], dropout=0.0, distance_metric=c["metric"]).to(dev)
+        layer.load_state_dict(c["sd"])
+        xd = x.to(dev).requires_grad_(True)
+        out = layer(xd, ei.to(dev))
+        (out * wout.to(dev)).sum().backward()
+        pclose(out, c["out"], msg=lambda m: f"{c['metric']} out: {m}")
+        pclose(xd.grad, c["dx"], scaled=True, msg=lambda m: f"{c['metric']} dx: {m}")
+        params = dict(layer.named_parameters())
+        for k, gref in c["grads"].items():
+            if gref is None:
+                continue
+            zero = k.endswith("k_linear.bias") and c["metric"] == "scaled_dot_product"     # analytically zero
+            pclose(params[k].grad, gref, scaled=True, atol=1e-4 if zero else 1e-5, msg=lambda m, k=k: f"d{k}: {m}")
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "scaled_dot_product"])
+def test_geo_layer_config3_snapshot_vs_oracle(dev, metric):
+    """One full config-3 snapshot (100 000 nodes, 2 000 000 edges, H = 128, 8 heads): the whole geometric layer forward
+    and backward against the CPU oracle on ALL rows (not a sample), CSR bit-exact."""
+    import tagan_b200
+    from tagan_b200 import ops
+    n, e, hidden, heads = 100_000, 2_000_000, 128, 8
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(n, hidden, generator=g)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    wout = torch.randn(n, hidden, generator=g)
+    torch.manual_seed(1)
+    layer = tagan_b200.TAGANGraphAttention(hidden, heads, dropout=0.0, distance_metric=metric).to(dev)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.geometric_attention.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    ref = R.geo_attention(xr, sd, ei, heads, metric)
+    (ref * wout).sum().backward()
+    csr = ops.build_csr(ei.to(dev), n)
+    o = R.build_csr(ei, n)
+    nnz = int(o["rowptr"][-1])
+    assert torch.equal(csr.rowptr.cpu(), torch.from_numpy(o["rowptr"])) and torch.equal(csr.col[:nnz].cpu(), torch.from_numpy(o["col"]))
+    xd = x.to(dev).requires_grad_(True)
+    out = layer(xd, csr)
+    (out * wout.to(dev)).sum().backward()
+    pclose(out, ref)
+    pclose(xd.grad, xr.grad, scaled=True)
+    for k, p in layer.geometric_attention.named_parameters():
+        zero = k == "k_linear.bias" and metric == "scaled_dot_product"
+        # weight gradients here are sums over 100k nodes / 2.1M entries: tolerance relative to their magnitude (x3)
+        pclose(p.grad, sd[k].grad, scaled=True, atol=1e-4 if zero else 3e-5, msg=lambda m, k=k: f"d{k}: {m}")
+
+
+def test_temporal_attention_config3_size_vs_oracle(dev):
+    """B = 100 000 nodes x T = 16 snapshots, H = 128, 8 heads, shared integer timestamps (+-10 band, RBF bias table): the
+    whole AsymmetricTemporalAttention forward + backward against the CPU oracle on every node."""
+    import tagan_b200
+    b, t, hidden, heads = 100_000, 16, 128, 8
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(b, t, hidden, generator=g)
+    wout = torch.randn(b, t, hidden, generator=g)
+    ts = torch.arange(t, dtype=torch.float32).repeat(b, 1)
+    torch.manual_seed(2)
+    m = tagan_b200.AsymmetricTemporalAttention(hidden, heads, dropout=0.0).to(dev)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.dim() == 1 or "table" in name or "kernel" in name:
+                p.add_(0.1 * torch.randn(p.shape, generator=g).to(dev))
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    ref = R.asym_temporal_attention(xr, sd, heads, time_stamps=ts)
+    (ref * wout).sum().backward()
+    xd = x.to(dev).requires_grad_(True)
+    out = m(xd, time_stamps=ts.to(dev))
+    (out * wout.to(dev)).sum().backward()
+    pclose(out, ref)
+    pclose(xd.grad, xr.grad, scaled=True)
+    zero = ("k_linear.bias", "time_q_proj.bias", "time_encoding.basis_proj.bias")
+    for k, p in m.named_parameters():
+        gref = sd[k].grad
+        if gref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        pclose(p.grad, gref, scaled=True, atol=2e-4 if k in zero else 3e-5, msg=lambda mm, k=k: f"d{k}: {mm}")
+
+
+def test_temporal_attention_per_node_timestamps_golden(dev, golden):
+    """Per-node (non-shared) timestamps against the reference: RBF time bias per node pair, global min/max normalisation,
+    +-10 band per node."""
+    import tagan_b200
+    for c in golden("tattn_per_node.pt"):
+        m = tagan_b200.AsymmetricTemporalAttention(c["hidden"], c["heads"], dropout=0.0, causal=c["causal"]).to(dev)
+        m.load_state_dict(c["sd"])
+        x = c["x"].to(dev).requires_grad_(True)
+        out, attn = m(x, time_stamps=c["ts"].to(dev), return_attention_weights=True)
+        (out * c["wout"].to(dev)).sum().backward()
+        name = c["name"]
+        pclose(out, c["out"], msg=lambda mm: f"{name} out: {mm}")
+        pclose(attn, c["attn"], kind="attention weights", msg=lambda mm: f"{name} attn: {mm}")
+        pclose(x.grad, c["dx"], scaled=True, msg=lambda mm: f"{name} dx: {mm}")
+        m.zero_grad(set_to_none=True)
+        x2 = c["x"].to(dev).requires_grad_(True)
+        out2 = m(x2, time_stamps=c["ts"].to(dev))                      # no weights requested: the fused layer path
+        (out2 * c["wout"].to(dev)).sum().backward()
+        pclose(out2, c["out"], msg=lambda mm: f"{name} out (fused): {mm}")
+        pclose(x2.grad, c["dx"], scaled=True, msg=lambda mm: f"{name} dx (fused): {mm}")
+        params = dict(m.named_parameters())
+        zero = ("k_linear.bias", "time_q_proj.bias", "time_encoding.basis_proj.bias")
+        for k, gref in c["grads"].items():
+            if gref is None:
+                assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0, (name, k)
+                continue
+            pclose(params[k].grad, gref, scaled=True, atol=1e-4 if k in zero else 1e-5, msg=lambda mm, k=k: f"{name} d{k}: {mm}")
