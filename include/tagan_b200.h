@@ -406,6 +406,60 @@ int tagan_scale_rows(const float* x, int64_t ldx, const float* rowscale, float* 
 int tagan_decay_scale(const float* ts, int64_t ldts, int32_t t, float* rowscale, int64_t rows,
                       tagan_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * After the hot path: pooling, classification head + loss, optimizer step -- one launch
+ * each, no host sync, so TAGAN.forward + backward + the trainer step capture into one CUDA graph.
+ *
+ * tagan_pack_padded_fwd/bwd: packed rows [sum N_t, H] + offsets[T+1] (int32) <-> zero-padded [T, maxn, H]; the pad + stack
+ *   of AsymmetricTemporalAttention.forward for ragged snapshots (temporal_attention.py:928-976).
+ * tagan_pool_blocks_fwd/bwd: out[t] = mean of logical rows [t*B, (t+1)*B) of x viewed as the row-major [B*T, H] matrix of
+ *   x[B,T,H] (time_major = 1: the storage is [T,B,H]) -- TAGAN.forward's node pooling (model.py:377-427; both of its branches
+ *   reduce to this block mean, including the `view(T,-1,H)` scrambling of node and time).
+ * tagan_head_fwd/bwd: TemporalClassificationHead with attention pooling (classification.py:743-975): Linear+Tanh+Linear(no
+ *   bias) scores -> softmax over T -> weighted sum -> Linear -> LayerNorm (ln_weight NULL: none) -> ReLU -> Linear, then
+ *   loss_type 0: binary_cross_entropy_with_logits mean over labels [label_rows, O] (label_rows == Bsz, or Bsz == 1 broadcast:
+ *   TemporalLossFunction :420-456), 1: cross entropy over class_index[Bsz] (model.py:436-438).  gf [Bsz,T,H].
+ *   Forward saves u [Bsz,T,H], alpha [Bsz,T], pooled/h1/hn [Bsz,H], stats [Bsz,2], logits [Bsz,O]; loss may be NULL.
+ *   Backward: dloss (device scalar, NULL = no loss term) and/or dlogits [Bsz,O]; dw holds the gradient buffers.
+ * tagan_adam_clip_step: *step += 1; clip = min(1, max_grad_norm / (sqrt(*grad_mean_sq * n) + 1e-6)) (max_grad_norm <= 0: off;
+ *   torch.nn.utils.clip_grad_norm_), then torch.optim.Adam's update (L2 weight decay, bias correction) on flat buffers
+ *   (trainer.py:295-311).  grad_mean_sq = tagan_mse_fwd of the flat gradient.
+ * ------------------------------------------------------------------------------------- */
+struct tagan_head_weights {
+  const float* attn0_weight; /* [H,H] */
+  const float* attn0_bias;   /* [H]   */
+  const float* attn2_weight; /* [H] (Linear(H,1,bias=False)) */
+  const float* fc0_weight;   /* [H,H] */
+  const float* fc0_bias;     /* [H]   */
+  const float* ln_weight;    /* [H] or NULL */
+  const float* ln_bias;      /* [H] or NULL */
+  const float* fc1_weight;   /* [O,H] */
+  const float* fc1_bias;     /* [O]   */
+};
+int tagan_pack_padded_fwd(const float* packed, const int32_t* offsets, float* padded, int32_t T, int32_t maxn, int32_t H,
+                          tagan_stream_t stream);
+int tagan_pack_padded_bwd(const float* dpadded, const int32_t* offsets, float* dpacked, int32_t T, int32_t maxn, int32_t H,
+                          tagan_stream_t stream);
+size_t tagan_pool_blocks_workspace_bytes(int32_t T, int32_t H);
+int tagan_pool_blocks_fwd(const float* x, int64_t B, int32_t T, int32_t H, int32_t time_major, float* out,
+                          void* workspace, size_t workspace_bytes, tagan_stream_t stream);
+int tagan_pool_blocks_bwd(const float* dout, int64_t B, int32_t T, int32_t H, int32_t time_major, float* dx,
+                          tagan_stream_t stream);
+int tagan_head_fwd(const struct tagan_head_weights* w, const float* gf, int32_t Bsz, int32_t T, int32_t H, int32_t O,
+                   int32_t loss_type, const float* labels, int32_t label_rows, const int64_t* class_index,
+                   float* u, float* alpha, float* pooled, float* h1, float* hn, float* stats, float* logits,
+                   float* loss, tagan_stream_t stream);
+size_t tagan_head_bwd_workspace_bytes(int32_t Bsz, int32_t T, int32_t H, int32_t O);
+int tagan_head_bwd(const struct tagan_head_weights* w, const float* gf, int32_t Bsz, int32_t T, int32_t H, int32_t O,
+                   int32_t loss_type, const float* labels, int32_t label_rows, const int64_t* class_index,
+                   const float* u, const float* alpha, const float* pooled, const float* h1, const float* hn,
+                   const float* stats, const float* logits, const float* dloss, const float* dlogits,
+                   float* dgf, struct tagan_head_weights* dw, void* workspace, size_t workspace_bytes,
+                   tagan_stream_t stream);
+int tagan_adam_clip_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                         const float* grad_mean_sq, int32_t* step, tagan_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,9 +11,12 @@ from .layers import (AsymmetricTemporalAttention, GeometricAttention, LayerNorm,
                      TemporalSkipConnection, TimeEncoding)
 
 from .memory_bank import NodeMemoryBank  # noqa: F401,E402
-from .model import TAGANLayer, forward_node_partitioned, patch  # noqa: F401,E402
+from .model import TAGANLayer, TAGANModel, forward_node_partitioned, patch  # noqa: F401,E402
+from .head import ClassificationModule, FusedAdam, TemporalClassificationHead  # noqa: F401,E402
+from .loader import PackedSequence, SequenceLoader  # noqa: F401,E402
 from .graphed import GraphedStep  # noqa: F401,E402
 
-__all__ = ["NodeMemoryBank", "TAGANLayer", "patch", "GraphedStep", "forward_node_partitioned", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
+__all__ = ["NodeMemoryBank", "TAGANLayer", "TAGANModel", "ClassificationModule", "TemporalClassificationHead", "FusedAdam",
+           "PackedSequence", "SequenceLoader", "patch", "GraphedStep", "forward_node_partitioned", "ops", "GeometricAttention", "TAGANGraphAttention", "AsymmetricTemporalAttention", "TimeEncoding",
            "TemporalGRUCell", "TemporalEvolutionLayer", "TemporalSkipConnection", "TemporalGatingUnit",
            "TemporalPropagation"]

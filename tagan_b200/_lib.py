@@ -27,6 +27,12 @@ class Epilogue(C.Structure):
 EPI_STORE, EPI_RES_LN, EPI_GATES, EPI_BLEND, EPI_GATES_BWD = range(5)
 
 
+class HeadWeights(C.Structure):
+    """struct tagan_head_weights (classification head parameters or their gradient buffers)"""
+    _fields_ = [(n, _p) for n in ("attn0_weight", "attn0_bias", "attn2_weight", "fc0_weight", "fc0_bias", "ln_weight", "ln_bias",
+                                  "fc1_weight", "fc1_bias")]
+
+
 class TimeParams(C.Structure):
     """struct tagan_time_params"""
     _fields_ = [("range", _p), ("mu", _p), ("inv2sig2", _p), ("wc", _p), ("bc", _p), ("nb", _i32)]
@@ -75,6 +81,17 @@ SIGNATURES = {
     "tagan_mse_workspace_bytes": (_sz, []),
     "tagan_mse_fwd": (_i32, [_p, _i64, _p, _p, _sz, _p]),
     "tagan_mse_bwd": (_i32, [_p, _i64, _p, _p, _p]),
+    "tagan_pack_padded_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _p]),
+    "tagan_pack_padded_bwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _p]),
+    "tagan_pool_blocks_workspace_bytes": (_sz, [_i32, _i32]),
+    "tagan_pool_blocks_fwd": (_i32, [_p, _i64, _i32, _i32, _i32, _p, _p, _sz, _p]),
+    "tagan_pool_blocks_bwd": (_i32, [_p, _i64, _i32, _i32, _i32, _p, _p]),
+    "tagan_head_fwd": (_i32, [C.POINTER(HeadWeights), _p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
+                              _p, _p]),
+    "tagan_head_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "tagan_head_bwd": (_i32, [C.POINTER(HeadWeights), _p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
+                              _p, _p, _p, C.POINTER(HeadWeights), _p, _sz, _p]),
+    "tagan_adam_clip_step": (_i32, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p, _p, _p]),
     "tagan_tattn_fwd": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _i64, _p, _i32, _f32, _p,
                                _p, _i32, _i32, _p, _p, _p, _p]),
     "tagan_tattn_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),

@@ -149,9 +149,11 @@ class _GeoLayerFn(torch.autograd.Function):
         r, hdim = rows.shape
         dev = rows.device
         t_steps = len(csrs)
-        n = csrs[0].num_nodes
-        if r != t_steps * n or any(c.num_nodes != n for c in csrs):
-            raise ValueError("geo_layer: rows must be T * N with the same N in every snapshot")
+        offs = [0]
+        for c in csrs:                                                            # snapshots may have different node counts
+            offs.append(offs[-1] + c.num_nodes)
+        if r != offs[-1]:
+            raise ValueError("geo_layer: the packed rows must be the concatenation of every snapshot's nodes")
         xn, mean1, rstd1 = _ln_plain(lib, rows, ln1w, ln1b)                        # :538-542
         w_qkv = torch.cat([wq, wk, wv], 0)
         b_qkv = torch.cat([bq, bk, bv], 0)
@@ -162,19 +164,19 @@ class _GeoLayerFn(torch.autograd.Function):
         ld = 3 * hdim
         base, cbase, lbase = qkv.data_ptr(), ctxv.data_ptr(), lse.data_ptr()
         for t, csr in enumerate(csrs):
-            off = base + t * n * ld * 4
+            off = base + offs[t] * ld * 4
             q, k, v = (C.c_void_p(off + i * hdim * 4) for i in range(3))
             ops.wait_csr(csr)
             with _timed("geo_attn_fwd"):
-                rc = lib.tagan_geo_attn_fwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), n, hdim, heads, metric,
-                                            _ptr(metric_param), C.c_void_p(cbase + t * n * hdim * 4),
-                                            C.c_void_p(lbase + t * n * heads * 4), None, _stream())
+                rc = lib.tagan_geo_attn_fwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), csr.num_nodes, hdim, heads, metric,
+                                            _ptr(metric_param), C.c_void_p(cbase + offs[t] * hdim * 4),
+                                            C.c_void_p(lbase + offs[t] * heads * 4), None, _stream())
             _lib.check(rc, "tagan_geo_attn_fwd")
         CALLS["n"] += t_steps
         need = any(ctx.needs_input_grad)
         out, xsum, mean2, rstd2 = linear_res_ln(ctxv, wo, bo, rows, ln2w, ln2b, need_sum=need)   # :586-596
         ctx.save_for_backward(rows, xn, mean1, rstd1, qkv, ctxv, lse, xsum, mean2, rstd2, ln1w, w_qkv, wo, ln2w, metric_param)
-        ctx.csrs, ctx.heads, ctx.metric, ctx.shape = csrs, heads, metric, x.shape
+        ctx.csrs, ctx.heads, ctx.metric, ctx.shape, ctx.offs = csrs, heads, metric, x.shape, offs
         return out.view(x.shape)
 
     @staticmethod
@@ -186,7 +188,8 @@ class _GeoLayerFn(torch.autograd.Function):
             raise RuntimeError("CSR was built without its transpose; backward needs it")
         r, hdim = rows.shape
         dev = rows.device
-        t_steps, n = len(csrs), csrs[0].num_nodes
+        t_steps, offs = len(csrs), ctx.offs
+        n = max(c.num_nodes for c in csrs)
         dout2 = _rows2(dout)
         d_o = _e(r, hdim, dev=dev)                                    # gradient of the pre-LN2 sum = of o AND of identity
         dln2w, dln2b = _ln_backward(lib, dout2, xsum, ln2w, mean2, rstd2, d_o, False)
@@ -202,15 +205,15 @@ class _GeoLayerFn(torch.autograd.Function):
         ld = 3 * hdim
         base, dbase = qkv.data_ptr(), dqkv.data_ptr()
         for t, csr in enumerate(csrs):
-            off, doff = base + t * n * ld * 4, dbase + t * n * ld * 4
+            off, doff = base + offs[t] * ld * 4, dbase + offs[t] * ld * 4
             q, k, v = (C.c_void_p(off + i * hdim * 4) for i in range(3))
             dq, dk, dv = (C.c_void_p(doff + i * hdim * 4) for i in range(3))
             with _timed("geo_attn_bwd"):
                 rc = lib.tagan_geo_attn_bwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.rowptr_t), _ptr(csr.row_t),
-                                            n, hdim, heads, metric, _ptr(metric_param),
-                                            C.c_void_p(ctxv.data_ptr() + t * n * hdim * 4),
-                                            C.c_void_p(lse.data_ptr() + t * n * heads * 4),
-                                            C.c_void_p(dctx.data_ptr() + t * n * hdim * 4), dq, dk, dv, ld, _ptr(delta),
+                                            csr.num_nodes, hdim, heads, metric, _ptr(metric_param),
+                                            C.c_void_p(ctxv.data_ptr() + offs[t] * hdim * 4),
+                                            C.c_void_p(lse.data_ptr() + offs[t] * heads * 4),
+                                            C.c_void_p(dctx.data_ptr() + offs[t] * hdim * 4), dq, dk, dv, ld, _ptr(delta),
                                             _ptr(dp_ws), C.c_void_p(dparam_t.data_ptr() + t * heads * 4) if want_dp else None,
                                             _stream())
             _lib.check(rc, "tagan_geo_attn_bwd")
@@ -227,7 +230,8 @@ class _GeoLayerFn(torch.autograd.Function):
 
 
 def geo_layer(ga, x, csrs):
-    """``GeometricAttention`` module ``ga`` over stacked snapshots: x ``[T*N,H]`` / ``[T,N,H]`` + T CSRs."""
+    """``GeometricAttention`` module ``ga`` over stacked snapshots: x ``[T*N,H]`` / ``[T,N,H]`` + T CSRs, or the PACKED
+    rows ``[sum N_t, H]`` of snapshots with different node counts (snapshot t's nodes are rows ``off[t]:off[t+1]``)."""
     return _GeoLayerFn.apply(x, ga.layer_norm1.weight, ga.layer_norm1.bias, ga.q_linear.weight, ga.q_linear.bias,
                              ga.k_linear.weight, ga.k_linear.bias, ga.v_linear.weight, ga.v_linear.bias,
                              ga.output_proj.weight, ga.output_proj.bias, ga.layer_norm2.weight, ga.layer_norm2.bias,

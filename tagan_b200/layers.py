@@ -347,24 +347,41 @@ class AsymmetricTemporalAttention(nn.Module):
         u8 = self._encode_mask(e4).expand(e4.shape[0], e4.shape[1], t, t).contiguous()
         return ops.TemporalMask(flags=flags, mask=u8)
 
+    def all_ones_mask_spec(self, t: int) -> "ops.TemporalMask":
+        """What :1142-1170 make of an all-ones ``[T,T]`` attention mask without timestamps (the only mask ``TAGAN.forward``
+        passes, model.py:336-361): it becomes ``[T,1,T] * tril -> [T,T,T]``, which broadcasts against ``[B,h,T,T]`` only when
+        ``T == num_heads`` (or T == 1) -- then every head is causal; otherwise the failed ``masked_fill`` is swallowed and
+        the scores stay unmasked."""
+        causal = self.causal or t == self.num_heads or t == 1
+        return ops.TemporalMask(flags=1 if causal else 0)
+
     # -- forward --------------------------------------------------------------------------
     def forward(self, x, time_stamps: Optional[torch.Tensor] = None, attention_mask=None,
-                return_attention_weights: bool = False, time_major: bool = False):
+                return_attention_weights: bool = False, time_major: bool = False,
+                resolved_mask: Optional["ops.TemporalMask"] = None):
         """``time_major=True`` (extension): ``x`` is the physical ``[T,B,H]`` stack of the per-snapshot tensors, i.e.
         what the list form is turned into anyway -- saves the stack copy; the result is the same ``[B,T,H]`` view."""
         if self.training and self.dropout_prob > 0 and not getattr(self, "_warned_attn_dropout", False):
             self._warned_attn_dropout = True
             warnings.warn(f"AsymmetricTemporalAttention: attention-weight dropout (p={self.dropout_prob}) is not applied by "
                           "the fused kernel in train() mode; output dropout is.  Use eval() or dropout=0 for reference parity.")
+        list_input = False
         if time_major and isinstance(x, torch.Tensor):
             phys = x.contiguous()
             t, b, hdim = phys.shape
         elif isinstance(x, list):                                     # :928-976
             cur = [t_[0] if isinstance(t_, list) and len(t_) > 0 else t_ for t_ in x]
             mx = max(t_.shape[0] for t_ in cur)
-            cur = [F.pad(t_, (0, 0, 0, mx - t_.shape[0])) if t_.shape[0] < mx else t_ for t_ in cur]
-            phys = torch.stack(cur, dim=0)                            # [T,B,H]; logical x = phys.permute(1,0,2)
+            if all(t_.shape[0] == mx for t_ in cur):
+                phys = ops.stack_rows(cur)                            # [T,B,H]; logical x = phys.permute(1,0,2)
+            else:
+                # ragged snapshots: one concatenation + ONE pad/stack launch (head.pack_padded) instead of T pads + a stack
+                from .head import pack_padded
+                sizes = [t_.shape[0] for t_ in cur]
+                offs = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0).tolist()), dtype=torch.int32).to(cur[0].device)
+                phys = pack_padded(torch.cat(cur, 0), offs, len(cur), mx)
             time_major = True
+            list_input = True
             t, b, hdim = phys.shape
         else:
             time_major = False
@@ -393,9 +410,13 @@ class AsymmetricTemporalAttention(nn.Module):
                 if b * t * t * max(nb, self.num_heads) > self.MAX_PER_NODE_BIAS_ELEMS:
                     raise NotImplementedError("per-node timestamps at this size are not supported yet")
                 bias = bias.unsqueeze(0) + self._time_bias(ts)
-        tmask = self._resolve_mask(attention_mask, ts, b, t, dev)
+        # resolved_mask (extension): the caller already applied the reference's mask rules (e.g. TAGANModel knows its mask is
+        # all ones), which skips the host read of `torch.all(mask == 1)` and keeps the call CUDA-graph capturable
+        tmask = resolved_mask if resolved_mask is not None else self._resolve_mask(attention_mask, ts, b, t, dev)
         if use_fused:
             out = fused.tattn_layer(self, rows, bias, tmask, b, t, time_major).view(phys.shape)
+            if list_input:             # the reference returns a CONTIGUOUS [maxN,T,H] (TAGAN.forward then calls .view on it)
+                return out.permute(1, 0, 2).contiguous()
             return out.permute(1, 0, 2) if time_major else out
         ctx, attn = ops.temporal_attention_core(qkv, bias, tmask, b, t, self.num_heads, time_major,
                                                 want_attn=return_attention_weights)
@@ -405,6 +426,8 @@ class AsymmetricTemporalAttention(nn.Module):
         out = out.view(phys.shape)
         if time_major:
             out = out.permute(1, 0, 2)
+            if list_input:
+                out = out.contiguous()
         return (out, attn) if return_attention_weights else out
 
 

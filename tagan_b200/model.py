@@ -124,3 +124,123 @@ def patch(model: nn.Module) -> nn.Module:
         model.memory_bank = NodeMemoryBank(cfg.hidden_dim, decay_factor=0.8, max_inactivity=cfg.temporal_window_size,
                                            device=dev)
     return model
+
+
+# ------------------------------------------------------------------------------------------
+# TAGAN.forward as a packed device pipeline
+# ------------------------------------------------------------------------------------------
+class TAGANModel(nn.Module):
+    """Stand-alone mirror of the reference ``TAGAN`` (src/tagan/model.py:22-473) with the SAME parameter names -- a
+    reference ``state_dict`` loads unchanged -- whose ``forward`` reproduces the observable behaviour of the shipped
+    ``TAGAN.forward`` as one packed device pipeline:
+
+    * all T snapshots' nodes are ONE packed matrix ``[sum N_t, .]``: node embedding, every LayerNorm / projection of the
+      geometric layers and the layer-0 skip (model.py:233-262) run once over all rows; kernel (a) runs per snapshot on row
+      ranges (snapshots may have different node counts);
+    * ``temporal_propagation`` is NOT called: the reference's call raises and falls back to the geometric outputs
+      (model.py:291-309, SURVEY.md fact 5); ``edge_embedding`` is ignored as in the reference (fact 3);
+    * temporal attention sees the zero-padded ``[T, maxN, H]`` stack (one pad/stack launch) with the reference's all-ones
+      mask (model.py:336-361: causal only when ``T == num_heads``, otherwise silently unmasked);
+    * node pooling with the reference's ``view`` scrambling (model.py:377-427), classification head and loss are one launch
+      each (``tagan_b200.head``).
+
+    ``config``: anything with the ``TAGANConfig`` attributes used here (a dict works)."""
+
+    def __init__(self, config):
+        super().__init__()
+        from .head import ClassificationModule
+        from types import SimpleNamespace
+        cfg = SimpleNamespace(**config) if isinstance(config, dict) else config
+        g = lambda k, d: getattr(cfg, k, d)  # noqa: E731
+        self.config = cfg
+        hd, heads, drop = cfg.hidden_dim, cfg.num_heads, g("dropout", 0.1)
+        self.hidden_dim, self.output_dim = hd, g("output_dim", 1)
+        use_ln = g("use_layer_norm", True)
+        learnable = g("learnable_distance", False)
+        self.node_embedding = nn.Linear(cfg.node_feature_dim, hd)
+        efd = g("edge_feature_dim", 0) if g("use_edge_features", True) else 0
+        self.edge_embedding = nn.Linear(efd, hd) if efd > 0 else None
+        metric = "scaled_dot_product" if learnable else "euclidean"                    # model.py:80
+        self.geometric_attention_layers = nn.ModuleList(
+            [TAGANGraphAttention(hd, heads, drop, metric, use_ln, learnable) for _ in range(g("num_layers", 2))])
+        self.temporal_propagation = TemporalPropagation(hd, hd, drop, g("time_aware", True), g("bidirectional", False), use_ln,
+                                                        g("use_skip_connection", True), g("use_gating", True),
+                                                        g("temporal_window_size", 3), g("aggregation_method", "mean"),
+                                                        g("use_residual", True))
+        self.temporal_attention = AsymmetricTemporalAttention(hd, heads, drop, causal=g("causal_attention", False), time_aware=True,
+                                                              use_layer_norm=use_ln, asymmetric_window_size=g("window_size", 5),
+                                                              relative_position_bias=g("asymmetric_temporal_bias", True))
+        self.classification_head = ClassificationModule(hd, self.output_dim, drop, use_ln)
+        self.skip_layer_norm = LayerNorm(hd) if use_ln else None
+        nn.init.xavier_uniform_(self.node_embedding.weight)
+        nn.init.zeros_(self.node_embedding.bias)
+        if self.edge_embedding is not None:
+            nn.init.xavier_uniform_(self.edge_embedding.weight)
+            nn.init.zeros_(self.edge_embedding.bias)
+
+    @staticmethod
+    def _unpack(snapshot):
+        if isinstance(snapshot, dict):
+            return snapshot["x"], snapshot["edge_index"]
+        if isinstance(snapshot, (tuple, list)) and len(snapshot) >= 4:
+            return snapshot[0], snapshot[1]
+        raise ValueError("snapshot must be a dict with keys x / edge_index / edge_attr / node_ids or a 4-tuple")
+
+    def forward(self, graph_sequence, labels=None):
+        """``graph_sequence``: list of T snapshots (dicts or ``(x, edge_index, edge_attr, node_ids)`` tuples, model.py:168-171),
+        or a ``tagan_b200.loader.PackedSequence`` already on the device.  Returns the reference's dict
+        (``logits``, ``predictions``, ``loss``)."""
+        from . import fused
+        from .head import pack_padded, pool_blocks
+        from .loader import PackedSequence
+        dev = self.node_embedding.weight.device
+        if isinstance(graph_sequence, PackedSequence):
+            seq = graph_sequence
+        else:
+            pairs = [self._unpack(s) for s in graph_sequence]
+            seq = PackedSequence.from_snapshots([p[0] for p in pairs], [p[1] for p in pairs]).to(dev)
+        t_steps, sizes, maxn = seq.num_snapshots, seq.sizes, seq.max_nodes
+        csrs = [ops.build_csr(seq.edge_index(t), sizes[t], transpose=torch.is_grad_enabled(), validate=False)
+                for t in range(t_steps)]
+        x = ops.linear(seq.x, self.node_embedding.weight, self.node_embedding.bias)                      # model.py:233
+        skip = x
+        for i, layer in enumerate(self.geometric_attention_layers):                                         # :244-262
+            ga = layer.geometric_attention
+            if ga._fused_ok():
+                x = fused.geo_layer(ga, x, csrs)
+            else:
+                x = torch.cat([ga.forward_csr(x[seq.offsets_host[t]:seq.offsets_host[t + 1]], csrs[t]) for t in range(t_steps)], 0)
+            if i == 0:
+                sk = self.skip_layer_norm(skip) if self.skip_layer_norm is not None else skip
+                x = ops.add(x, sk)
+        # temporal propagation: the reference's call never completes and falls back to x (model.py:291-309)
+        if len(set(sizes)) == 1:
+            phys = x.view(t_steps, maxn, self.hidden_dim)
+        else:
+            phys = pack_padded(x, seq.offsets, t_steps, maxn)                                                # temporal_attention.py:928-976
+        # model.py:336-361 passes ones(T,T): resolved on the host from the shapes alone (no device read, graph-capturable)
+        out = self.temporal_attention(phys, time_major=True,
+                                      resolved_mask=self.temporal_attention.all_ones_mask_spec(t_steps))   # [maxN,T,H] view of [T,maxN,H]
+        gf = pool_blocks(out.permute(1, 0, 2), maxn, t_steps, True)                                          # model.py:377-427
+        bsz = 1
+        if labels is not None and labels.dim() > 0:
+            bsz = labels.shape[0]
+        if bsz > 1:                                   # graph_features rows beyond the first stay zero in the reference
+            gf3 = torch.cat([gf.unsqueeze(0), torch.zeros(bsz - 1, t_steps, self.hidden_dim, device=dev)], 0)
+        else:
+            gf3 = gf.unsqueeze(0)
+        head = self.classification_head.classification_head
+        lab = cls = None
+        if labels is not None:
+            labels = labels.to(dev)
+            if labels.dtype == torch.bool:
+                labels = labels.long()
+            if self.output_dim > 1 and labels.dim() == 1:                                                    # model.py:436-438
+                cls = labels.long().contiguous()
+            else:                                                                                            # TemporalLossFunction :420-456
+                lab = labels.float().reshape(-1, self.output_dim) if labels.numel() % self.output_dim == 0 else None
+                if lab is None or (lab.shape[0] != bsz and bsz != 1):
+                    raise ValueError(f"Predictions shape {(bsz, self.output_dim)} does not match targets shape {tuple(labels.shape)}")
+        logits, loss = head.forward_loss(gf3, lab, cls)
+        predictions = torch.sigmoid(logits) if self.output_dim == 1 else torch.softmax(logits, dim=1)        # :447-459
+        return {"logits": logits, "predictions": predictions, "loss": loss}

@@ -1,0 +1,208 @@
+"""GPU: everything after the hot path -- pad/stack of ragged snapshots, node pooling, classification head
++ loss, optimizer step -- against torch restatements of the reference code, and the WHOLE model (``TAGANModel``: packed
+device pipeline with the reference's fallback behaviour) against the outputs and autograd gradients of the unmodified
+reference ``TAGAN.forward`` (tests/golden/tagan_model.pt, three configurations incl. the T == num_heads causal quirk)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from parity_util import close as pclose
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_pack_padded_and_pool_blocks(dev):
+    from tagan_b200.head import pack_padded, pool_blocks
+    torch.manual_seed(0)
+    sizes, h = [5, 9, 1, 7], 32
+    xs = [torch.randn(n, h, device=dev, requires_grad=True) for n in sizes]
+    offs = torch.tensor([0, 5, 14, 15, 22], dtype=torch.int32, device=dev)
+    out = pack_padded(torch.cat(xs, 0), offs, 4, 9)
+    ref = torch.stack([F.pad(x, (0, 0, 0, 9 - x.shape[0])) for x in xs], 0)
+    assert torch.equal(out, ref)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    for x, n, t in zip(xs, sizes, range(4)):
+        assert torch.equal(x.grad, w[t, :n])
+    # pooling: block means of the [B*T, H] row-major view of x[B,T,H], from either storage order (model.py:377-427)
+    for b, t in ((9, 4), (4, 4), (1000, 16), (7, 3)):
+        x = torch.randn(b, t, h, device=dev)
+        ref = x.reshape(t, -1, h).mean(1)
+        xa = x.clone().requires_grad_(True)
+        got = pool_blocks(xa, b, t, False)
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+        xt = x.permute(1, 0, 2).contiguous().requires_grad_(True)                       # time-major storage [T,B,H]
+        got_t = pool_blocks(xt, b, t, True)
+        torch.testing.assert_close(got_t, ref, rtol=1e-5, atol=1e-6)
+        g = torch.randn(t, h, device=dev)
+        xr = x.clone().requires_grad_(True)
+        (xr.reshape(t, -1, h).mean(1) * g).sum().backward()
+        (got * g).sum().backward()
+        (got_t * g).sum().backward()
+        torch.testing.assert_close(xa.grad, xr.grad, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(xt.grad.permute(1, 0, 2), xr.grad, rtol=1e-5, atol=1e-7)
+
+
+class _RefHead(nn.Module):
+    """torch restatement of TemporalClassificationHead (attention pooling, 2 layers) -- classification.py:743-975"""
+
+    def __init__(self, h, o, use_ln):
+        super().__init__()
+        self.attention = nn.Sequential(nn.Linear(h, h), nn.Tanh(), nn.Linear(h, 1, bias=False))
+        layers = [nn.Linear(h, h)] + ([nn.LayerNorm(h)] if use_ln else []) + [nn.ReLU(), nn.Dropout(0.0), nn.Linear(h, o)]
+        self.classifier = nn.Sequential(*layers)
+
+    def forward(self, x):
+        a = torch.softmax(self.attention(x), dim=1)
+        return self.classifier((x * a).sum(1))
+
+
+@pytest.mark.parametrize("bsz,t,h,o,use_ln,loss", [(1, 5, 64, 1, True, "bce"), (3, 16, 32, 4, True, "bce"), (2, 7, 40, 5, False, "ce"),
+                                                     (1, 1, 16, 1, True, "bce"), (1, 128, 128, 1, True, "bce_bcast")])
+def test_head_vs_torch(dev, bsz, t, h, o, use_ln, loss):
+    from tagan_b200.head import TemporalClassificationHead
+    torch.manual_seed(bsz * 100 + t)
+    ref = _RefHead(h, o, use_ln).double()
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    head = TemporalClassificationHead(h, o, dropout=0.0, use_layer_norm=use_ln).to(dev)
+    head.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    x = torch.randn(bsz, t, h)
+    xr = x.double().requires_grad_(True)
+    xd = x.to(dev).requires_grad_(True)
+    logits_ref = ref(xr)
+    if loss == "ce":
+        cls = torch.randint(0, o, (bsz,))
+        loss_ref = F.cross_entropy(logits_ref, cls)
+        logits, l = head.forward_loss(xd, None, cls.to(dev))
+    elif loss == "bce_bcast":                                  # predictions [1,1] against targets [4,1] (TemporalLossFunction :436-438)
+        y = torch.tensor([[1.0], [0.0], [1.0], [1.0]])
+        loss_ref = F.binary_cross_entropy_with_logits(logits_ref.expand(4, -1), y.double())
+        logits, l = head.forward_loss(xd, y.to(dev), None)
+    else:
+        y = torch.rand(bsz, o).round()
+        loss_ref = F.binary_cross_entropy_with_logits(logits_ref, y.double())
+        logits, l = head.forward_loss(xd, y.to(dev), None)
+    (loss_ref * 2.0 + (logits_ref * 0.3).sum()).backward()
+    (l * 2.0 + (logits * 0.3).sum()).backward()
+    pclose(logits, logits_ref.float())
+    pclose(l, loss_ref.float())
+    pclose(xd.grad, xr.grad.float(), scaled=True)
+    gref = dict(ref.named_parameters())
+    for k, p in head.named_parameters():
+        pclose(p.grad, gref[k].grad.float(), scaled=True, msg=lambda m, k=k: f"d{k}: {m}")
+
+
+def test_fused_adam_matches_torch(dev):
+    """clip_grad_norm_ + torch.optim.Adam (reference trainer.py:295-311) over several steps."""
+    from tagan_b200 import FusedAdam
+    torch.manual_seed(3)
+    shapes = [(64, 16), (64,), (7,), (128, 64), (1, 64)]
+    p_ref = [nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    p_new = [nn.Parameter(p.detach().clone()) for p in p_ref]
+    opt_ref = torch.optim.Adam(p_ref, lr=1e-2, weight_decay=1e-3)
+    opt = FusedAdam(p_new, lr=1e-2, weight_decay=1e-3, max_grad_norm=0.5)
+    for step in range(6):
+        grads = [torch.randn(s, device=dev) * (3.0 if step % 2 else 0.05) for s in shapes]      # clipped and unclipped steps
+        opt_ref.zero_grad()
+        opt.zero_grad()
+        for p, q, g in zip(p_ref, p_new, grads):
+            p.grad = g.clone()
+            q.grad.add_(g)                                     # accumulate into the flat view, as autograd does
+        nrm = torch.nn.utils.clip_grad_norm_(p_ref, 0.5)
+        opt_ref.step()
+        opt.step()
+        assert abs(opt.grad_norm() - float(nrm)) < 1e-4 * max(1.0, float(nrm))
+        for p, q in zip(p_ref, p_new):
+            torch.testing.assert_close(q.detach(), p.detach(), rtol=1e-5, atol=1e-6)
+    assert int(opt.step_dev.item()) == 6
+
+
+def _cfg(c):
+    return dict(c["cfg"])
+
+
+def test_whole_model_vs_reference_golden(dev, golden):
+    """TAGAN.forward of the unmodified reference on the example.py shapes (ragged snapshots, 5..10 nodes, T = 5; hidden 64 /
+    4 heads, learnable-distance variant, and 5 heads == T where the all-ones mask becomes causal): logits, loss and EVERY
+    parameter gradient -- including which parameters get none (edge embedding, temporal propagation, time encoding)."""
+    import tagan_b200
+    for c in golden("tagan_model.pt"):
+        model = tagan_b200.TAGANModel(_cfg(c)).to(dev)
+        model.load_state_dict(c["sd"])
+        model.eval()
+        seq = [(x.to(dev), ei.to(dev), ea, ids) for x, ei, ea, ids in c["seq"]]
+        out = model(seq, c["labels"].to(dev))
+        out["loss"].backward()
+        tag = f"heads={c['cfg']['num_heads']} learnable={c['cfg']['learnable_distance']}"
+        pclose(out["logits"], c["logits"], msg=lambda m: f"{tag} logits: {m}")
+        pclose(out["loss"], c["loss"], msg=lambda m: f"{tag} loss: {m}")
+        torch.testing.assert_close(out["predictions"].cpu(), torch.sigmoid(c["logits"]), rtol=1e-4, atol=1e-5)
+        params = dict(model.named_parameters())
+        assert set(params) == set(c["grads"]), set(params) ^ set(c["grads"])
+        for k, gref in c["grads"].items():
+            g = params[k].grad
+            if gref is None:
+                assert g is None or float(g.abs().max()) == 0.0, (tag, k)
+            else:
+                assert g is not None, (tag, k)
+                zero = k.endswith("k_linear.bias")             # analytically zero for sdp scores (softmax shift invariance)
+                pclose(g, gref, scaled=True, atol=1e-4 if zero else 1e-5, msg=lambda m, k=k: f"{tag} d{k}: {m}")
+        # dict-format snapshots and the packed wire format give the same numbers
+        seq_d = [{"x": x.to(dev), "edge_index": ei.to(dev), "edge_attr": ea, "node_ids": ids} for x, ei, ea, ids in c["seq"]]
+        packed = tagan_b200.PackedSequence.from_snapshots([s[0] for s in c["seq"]], [s[1] for s in c["seq"]]).to(dev)
+        assert torch.equal(model(seq_d, c["labels"].to(dev))["logits"], out["logits"])
+        assert torch.equal(model(packed, c["labels"].to(dev))["logits"], out["logits"])
+
+
+def test_train_step_graph_replay_matches_eager(dev, golden):
+    """forward + loss + backward + clip + Adam captured as ONE CUDA graph: three replays == three eager steps."""
+    import tagan_b200
+    from tagan_b200.head import TrainStep
+    c = golden("tagan_model.pt")[0]
+    packed = tagan_b200.PackedSequence.from_snapshots([s[0] for s in c["seq"]], [s[1] for s in c["seq"]]).to(dev)
+    labels = c["labels"].to(dev)
+    losses = {}
+    finals = {}
+    for mode in ("eager", "graph"):
+        model = tagan_b200.TAGANModel(_cfg(c)).to(dev)
+        model.load_state_dict(c["sd"])
+        model.eval()
+        opt = tagan_b200.FusedAdam(list(model.parameters()), lr=1e-3, max_grad_norm=1.0)
+        step = TrainStep(model, opt)
+        if mode == "graph":
+            step.capture(packed, labels)
+            losses[mode] = [float(step.replay()) for _ in range(3)]
+        else:
+            losses[mode] = [float(step.eager(packed, labels)) for _ in range(3)]
+        finals[mode] = opt.flat.clone()
+    assert losses["eager"][0] > losses["eager"][2]             # it trains
+    assert abs(losses["eager"][0] - float(c["loss"])) < 1e-5
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) < 1e-6, (losses)
+    torch.testing.assert_close(finals["graph"], finals["eager"], rtol=1e-6, atol=1e-7)
+
+
+def test_sequence_loader_prefetch(dev, tmp_path):
+    import tagan_b200
+    torch.manual_seed(0)
+    seqs = []
+    for i in range(3):
+        xs = [torch.randn(4 + i, 8) for _ in range(3)]
+        es = [torch.randint(0, 4 + i, (2, 10)) for _ in range(3)]
+        seqs.append(tagan_b200.PackedSequence.from_snapshots(xs, es, pin=True))
+    path = str(tmp_path / "seq0.tagan")
+    seqs[0].save(path)
+    got = list(tagan_b200.SequenceLoader([path, seqs[1], seqs[2]], dev))
+    assert len(got) == 3
+    torch.cuda.synchronize()
+    for g, s in zip(got, seqs):
+        assert g.x.is_cuda and torch.equal(g.x.cpu(), s.x) and torch.equal(g.edges.cpu(), s.edges)
+        assert g.offsets_host == s.offsets_host and torch.equal(g.offsets.cpu(), s.offsets)
