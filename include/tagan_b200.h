@@ -407,6 +407,41 @@ int tagan_decay_scale(const float* ts, int64_t ldts, int32_t t, float* rowscale,
                       tagan_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (b2) RBF time bias for PER-NODE timestamps (AsymmetricTemporalAttention._compute_time_based_attention,
+ * temporal_attention.py:792-871, with TimeEncoding._get_basis_encoding :122-220), on device and chunk by chunk:
+ *   tagan_ts_range: *range = max over nodes of (max_t ts - min_t ts); the reference's global min / max of all pairwise
+ *     differences (:142-152) are -range and +range.
+ *   tagan_time_bias_fwd: for nodes [node_begin, node_begin+nodes): bias[b,h,i,j] = pos_bias[h,i,j] + bc[h] +
+ *     sum_k wc[h,k] exp(clamp(-(tn-mu_k)^2/(2 sigma_k^2), -88, 88)), tn = (ts_i - ts_j + range) / (2 range) (0 if the
+ *     range is degenerate); bias_t is the (j,i) transpose.  wc = time_q_proj.weight @ basis_proj.weight (time_k_proj is
+ *     unused, :848).  The tiles feed tagan_tattn_fwd/bwd_strided with bias_bstride = heads*T*T.
+ *   tagan_time_bias_bwd: dbias tile of the same nodes -> dparams (+)= [heads*nb d wc | heads d bc | nb d mu | nb d sigma],
+ *     dpos (+)= sum_b dbias (optional).  Deterministic (fixed-order partials).
+ * tagan_tattn_fwd/bwd_strided: as tagan_tattn_fwd/bwd with the row strides of the node and snapshot axes given explicitly
+ *   (row of (node b, step t) = b*row_stride_b + t*row_stride_t), so a chunk of nodes of a time-major tensor can be addressed.
+ * ------------------------------------------------------------------------------------- */
+int tagan_ts_range(const float* ts, int64_t B, int32_t T, float* range, tagan_stream_t stream);
+int tagan_time_bias_fwd(const float* ts, int64_t node_begin, int64_t nodes, int32_t T, int32_t heads, int32_t num_bases,
+                        const float* range, const float* mu, const float* sigma, const float* wc, const float* bc,
+                        const float* pos_bias, float* bias, float* bias_t, tagan_stream_t stream);
+size_t tagan_time_bias_bwd_workspace_bytes(int32_t heads, int32_t num_bases);
+int tagan_time_bias_bwd(const float* ts, int64_t node_begin, int64_t nodes, int32_t T, int32_t heads, int32_t num_bases,
+                        const float* range, const float* mu, const float* sigma, const float* wc, const float* dbias,
+                        float* dparams, float* dpos, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                        tagan_stream_t stream);
+int tagan_tattn_fwd_strided(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
+                            int32_t H, int32_t heads, int64_t row_stride_b, int64_t row_stride_t, const float* bias,
+                            const float* bias_t, int64_t bias_bstride, const float* ts, int32_t mask_flags, float band,
+                            const int32_t* allones_flag, const uint8_t* mask, int32_t mask_b, int32_t mask_h,
+                            float* ctx, float* lse, float* attn, tagan_stream_t stream);
+int tagan_tattn_bwd_strided(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
+                            int32_t H, int32_t heads, int64_t row_stride_b, int64_t row_stride_t, const float* bias,
+                            const float* bias_t, int64_t bias_bstride, const float* ts, int32_t mask_flags, float band,
+                            const int32_t* allones_flag, const uint8_t* mask, int32_t mask_b, int32_t mask_h,
+                            const float* ctx, const float* lse, const float* dctx, float* dQ, float* dK, float* dV,
+                            int64_t ldd, float* dbias, void* workspace, size_t workspace_bytes, tagan_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * After the hot path: pooling, classification head + loss, optimizer step -- one launch
  * each, no host sync, so TAGAN.forward + backward + the trainer step capture into one CUDA graph.
  *

@@ -8,7 +8,7 @@ REFERENCE (imported from /root/reference in the build container):
 * ``geo_c2_powerlaw.pt``  one config-2-shaped snapshot (N = 10 000, ~200 k power-law edges, H = 128, 4 heads) through
   the reference's DENSE ``TAGANGraphAttention`` (scaled_dot_product; 5.5 GB, a few seconds), forward and backward,
   plus a 1 200-node power-law snapshot for the default ``euclidean`` metric (whose dense backward is a Python loop).
-  Outputs are stored; the inputs are re-generated from the recorded seeds by the same torch CPU generator.
+  Outputs and the edge list are stored; x is re-created by an integer hash (bit-identical on any machine).
 * ``tattn_per_node.pt``   AsymmetricTemporalAttention with PER-NODE timestamps (the in-kernel RBF time bias).
 """
 import os
@@ -21,14 +21,28 @@ from oracle import ref_loader  # noqa: E402
 from oracle.make_golden import OUT, _grads, _randomize, _sd  # noqa: E402
 
 
-def powerlaw_inputs(n, e, hidden, seed):
-    """Deterministic inputs of the power-law cases (shared by the generator and the tests)."""
+def hashed_uniform(shape, salt: int) -> torch.Tensor:
+    """Deterministic values in [-1, 1) from INTEGER arithmetic only (bit-identical on every CPU; torch.randn is not: its
+    vectorised and scalar paths differ between machines), so fixtures can re-create large inputs instead of storing them."""
+    n = 1
+    for s_ in shape:
+        n *= s_
+    i = torch.arange(n, dtype=torch.int64) + salt * 1_000_003
+    i = (i * 2654435761) % 4294967296
+    i = ((i ^ (i >> 15)) * 2246822519) % 4294967296
+    i = ((i ^ (i >> 13)) * 3266489917) % 4294967296
+    i = i ^ (i >> 16)
+    return ((i % 65536).float() / 32768.0 - 1.0).reshape(shape)
+
+
+def powerlaw_inputs(n, hidden, seed):
+    """x and the output weighting of the power-law cases (shared by the generator and the tests); the edge list is stored."""
+    return 1.5 * hashed_uniform((n, hidden), seed), hashed_uniform((n, hidden), seed + 1)
+
+
+def powerlaw_edges(n, e, seed):
     from tagan_b200.synth import random_edges
-    g = torch.Generator().manual_seed(seed)
-    ei = random_edges(n, e, g, "powerlaw")
-    x = torch.randn(n, hidden, generator=g)
-    wout = torch.randn(n, hidden, generator=g)
-    return x, ei, wout
+    return random_edges(n, e, torch.Generator().manual_seed(seed), "powerlaw")
 
 
 def prop_cases(ref):
@@ -79,7 +93,8 @@ def geo_powerlaw_cases(ref):
     cases = []
     for (n, e, hidden, heads, metric, seed) in ((10_000, 200_000, 128, 4, "scaled_dot_product", 7001),
                                                 (1_200, 24_000, 128, 4, "euclidean", 7002)):
-        x, ei, wout = powerlaw_inputs(n, e, hidden, seed)
+        x, wout = powerlaw_inputs(n, hidden, seed)
+        ei = powerlaw_edges(n, e, seed)
         torch.manual_seed(seed)
         layer = ref.TAGANGraphAttention(hidden, num_heads=heads, dropout=0.0, distance_metric=metric)
         _randomize(layer, seed % 97)
@@ -90,8 +105,8 @@ def geo_powerlaw_cases(ref):
             (out * wout).sum().backward()
         deg = torch.bincount(ei[0], minlength=n)
         cases.append(dict(n=n, e=e, hidden=hidden, heads=heads, metric=metric, seed=seed, sd=_sd(layer),
-                          out=out.detach().clone(), dx=xr.grad.clone(), grads=_grads(layer), max_degree=int(deg.max()),
-                          x_checksum=float(x.double().sum()), ei_checksum=int(ei.sum())))
+                          edge_index=ei.to(torch.int32), out=out.detach().clone(), dx=xr.grad.clone(), grads=_grads(layer),
+                          max_degree=int(deg.max()), x_checksum=float(x.double().sum())))
         print("geo powerlaw", n, metric, "max raw degree", int(deg.max()))
     return cases
 
@@ -118,10 +133,44 @@ def tattn_per_node_cases(ref):
     return cases
 
 
+def model_cases(ref):
+    """Whole ``TAGAN.forward`` with T == num_heads == 4 (the all-ones temporal mask then broadcasts and becomes CAUSAL,
+    model.py:336-361 + temporal_attention.py:1142-1170) and with equal-sized snapshots; complements tagan_model.pt, whose
+    T == heads case uses 5 heads (a head count the geometric kernel does not support: power-of-two head dims only)."""
+    import numpy as np
+    out = []
+    for name, t_steps, sizes, heads, hidden, out_dim in (("t4_h4_ragged", 4, None, 4, 64, 1), ("t6_h8_equal", 6, 12, 8, 64, 1),
+                                                         ("t4_h4_multiclass", 4, None, 4, 32, 3)):
+        torch.manual_seed(3)
+        np.random.seed(3)
+        cfg = dict(node_feature_dim=16, edge_feature_dim=8, hidden_dim=hidden, num_heads=heads, num_layers=2, output_dim=out_dim,
+                   dropout=0.0, loss_type="bce", use_edge_features=True, learnable_distance=False, temporal_window_size=3)
+        with ref_loader.quiet():
+            model = ref.TAGAN(ref.TAGANConfig(**cfg))
+        _randomize(model, 31)
+        model.eval()
+        seq = []
+        for _ in range(t_steps):
+            nt = sizes if sizes is not None else int(np.random.randint(5, 11))
+            x = torch.randn(nt, 16)
+            ei = torch.randint(0, nt, (2, 3 * nt))
+            seq.append((x, ei, torch.randn(3 * nt, 8), list(range(nt))))
+        labels = torch.tensor([1]) if out_dim > 1 else torch.tensor([[1.0]])
+        with ref_loader.quiet():
+            res = model(seq, labels)
+            res["loss"].backward()
+        out.append(dict(name=name, cfg=cfg, seq=seq, labels=labels, sd=_sd(model), logits=res["logits"].detach().clone(),
+                        loss=res["loss"].detach().clone(), predictions=res["predictions"].detach().clone(), grads=_grads(model)))
+        print("model case", name, "loss", float(res["loss"]))
+    return out
+
+
 def main():
     ref = ref_loader.load()
     torch.set_num_threads(8)
-    which = set(sys.argv[1:]) or {"prop", "geo", "tattn"}
+    which = set(sys.argv[1:]) or {"prop", "geo", "tattn", "model"}
+    if "model" in which:
+        torch.save(model_cases(ref), os.path.join(OUT, "tagan_model_r02.pt"))
     if "prop" in which:
         torch.save(prop_cases(ref), os.path.join(OUT, "propagation_h32.pt"))
     if "tattn" in which:

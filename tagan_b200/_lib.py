@@ -81,6 +81,14 @@ SIGNATURES = {
     "tagan_mse_workspace_bytes": (_sz, []),
     "tagan_mse_fwd": (_i32, [_p, _i64, _p, _p, _sz, _p]),
     "tagan_mse_bwd": (_i32, [_p, _i64, _p, _p, _p]),
+    "tagan_ts_range": (_i32, [_p, _i64, _i32, _p, _p]),
+    "tagan_time_bias_fwd": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "tagan_time_bias_bwd_workspace_bytes": (_sz, [_i32, _i32]),
+    "tagan_time_bias_bwd": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _sz, _p]),
+    "tagan_tattn_fwd_strided": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _p, _p, _i64, _p, _i32, _f32, _p,
+                                       _p, _i32, _i32, _p, _p, _p, _p]),
+    "tagan_tattn_bwd_strided": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _p, _p, _i64, _p, _i32, _f32, _p,
+                                       _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _sz, _p]),
     "tagan_pack_padded_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _p]),
     "tagan_pack_padded_bwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _p]),
     "tagan_pool_blocks_workspace_bytes": (_sz, [_i32, _i32]),

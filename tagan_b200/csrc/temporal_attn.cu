@@ -354,12 +354,12 @@ int bwd_grid(int64_t B) { return (int)(B < 148 * 4 ? B : 148 * 4); }
 
 }  // namespace
 
-TAGAN_API int tagan_tattn_fwd(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
-                              int32_t H, int32_t heads, int32_t time_major, const float* bias, const float* bias_t,
-                              int64_t bias_bstride, const float* ts,
-                              int32_t mask_flags, float band, const int32_t* allones_flag, const uint8_t* mask,
-                              int32_t mask_b, int32_t mask_h, float* ctx, float* lse, float* attn,
-                              tagan_stream_t stream) {
+static int tattn_fwd_impl(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
+                          int32_t H, int32_t heads, int64_t rsb, int64_t rst, const float* bias, const float* bias_t,
+                          int64_t bias_bstride, const float* ts,
+                          int32_t mask_flags, float band, const int32_t* allones_flag, const uint8_t* mask,
+                          int32_t mask_b, int32_t mask_h, float* ctx, float* lse, float* attn,
+                          tagan_stream_t stream) {
   if (!Q || !K || !V || !ctx || !lse || B < 0 || ld < H) return TAGAN_E_INVALID;
   if ((mask_flags & 2) && !ts) return TAGAN_E_INVALID;
   if ((mask_flags & 4) && !allones_flag) return TAGAN_E_INVALID;
@@ -370,7 +370,6 @@ TAGAN_API int tagan_tattn_fwd(const float* Q, const float* K, const float* V, in
   if (!make_cfg(T, D, heads, 2 * T * D + ((T + 3) & ~3), &c)) return TAGAN_E_UNSUPPORTED;
   MaskSpec ms{ts, mask_flags, band, allones_flag, mask, mask_b, mask_h};
   const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
-  const int64_t rsb = time_major ? 1 : T, rst = time_major ? B : 1;
   cudaStream_t st = as_stream(stream);
   int rc = 0;
   switch (D) {
@@ -393,13 +392,33 @@ TAGAN_API int tagan_tattn_fwd(const float* Q, const float* K, const float* V, in
   return tagan_launch_status();
 }
 
+TAGAN_API int tagan_tattn_fwd(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
+                              int32_t H, int32_t heads, int32_t time_major, const float* bias, const float* bias_t,
+                              int64_t bias_bstride, const float* ts,
+                              int32_t mask_flags, float band, const int32_t* allones_flag, const uint8_t* mask,
+                              int32_t mask_b, int32_t mask_h, float* ctx, float* lse, float* attn,
+                              tagan_stream_t stream) {
+  return tattn_fwd_impl(Q, K, V, ld, B, T, H, heads, time_major ? 1 : T, time_major ? B : 1, bias, bias_t, bias_bstride, ts,
+                        mask_flags, band, allones_flag, mask, mask_b, mask_h, ctx, lse, attn, stream);
+}
+
+TAGAN_API int tagan_tattn_fwd_strided(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
+                                      int32_t H, int32_t heads, int64_t row_stride_b, int64_t row_stride_t, const float* bias,
+                                      const float* bias_t, int64_t bias_bstride, const float* ts, int32_t mask_flags, float band,
+                                      const int32_t* allones_flag, const uint8_t* mask, int32_t mask_b, int32_t mask_h,
+                                      float* ctx, float* lse, float* attn, tagan_stream_t stream) {
+  if (row_stride_b <= 0 || row_stride_t <= 0) return TAGAN_E_INVALID;
+  return tattn_fwd_impl(Q, K, V, ld, B, T, H, heads, row_stride_b, row_stride_t, bias, bias_t, bias_bstride, ts, mask_flags,
+                        band, allones_flag, mask, mask_b, mask_h, ctx, lse, attn, stream);
+}
+
 TAGAN_API size_t tagan_tattn_bwd_workspace_bytes(int64_t B, int32_t T, int32_t heads) {
   if (B < 0 || T <= 0 || heads <= 0) return 0;
   return (size_t)bwd_grid(B) * heads * (size_t)T * T * sizeof(float);
 }
 
-TAGAN_API int tagan_tattn_bwd(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
-                              int32_t H, int32_t heads, int32_t time_major, const float* bias, const float* bias_t, int64_t bias_bstride,
+static int tattn_bwd_impl(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
+                          int32_t H, int32_t heads, int64_t rsb, int64_t rst, const float* bias, const float* bias_t, int64_t bias_bstride,
                               const float* ts, int32_t mask_flags, float band, const int32_t* allones_flag,
                               const uint8_t* mask, int32_t mask_b, int32_t mask_h, const float* ctx, const float* lse,
                               const float* dctx, float* dQ, float* dK, float* dV, int64_t ldd, float* dbias,
@@ -427,7 +446,6 @@ TAGAN_API int tagan_tattn_bwd(const float* Q, const float* K, const float* V, in
     }
   }
   MaskSpec ms{ts, mask_flags, band, allones_flag, mask, mask_b, mask_h};
-  const int64_t rsb = time_major ? 1 : T, rst = time_major ? B : 1;
   cudaStream_t st = as_stream(stream);
   int rc = 0;
   switch (D) {
@@ -451,6 +469,28 @@ TAGAN_API int tagan_tattn_bwd(const float* Q, const float* K, const float* V, in
     reduce_parts<<<ceil_div_i64(n, 256), 256, 0, st>>>(db_target, grid, n, dbias);
   }
   return tagan_launch_status();
+}
+
+TAGAN_API int tagan_tattn_bwd(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
+                              int32_t H, int32_t heads, int32_t time_major, const float* bias, const float* bias_t, int64_t bias_bstride,
+                              const float* ts, int32_t mask_flags, float band, const int32_t* allones_flag,
+                              const uint8_t* mask, int32_t mask_b, int32_t mask_h, const float* ctx, const float* lse,
+                              const float* dctx, float* dQ, float* dK, float* dV, int64_t ldd, float* dbias,
+                              void* workspace, size_t workspace_bytes, tagan_stream_t stream) {
+  return tattn_bwd_impl(Q, K, V, ld, B, T, H, heads, time_major ? 1 : T, time_major ? B : 1, bias, bias_t, bias_bstride, ts,
+                        mask_flags, band, allones_flag, mask, mask_b, mask_h, ctx, lse, dctx, dQ, dK, dV, ldd, dbias, workspace,
+                        workspace_bytes, stream);
+}
+
+TAGAN_API int tagan_tattn_bwd_strided(const float* Q, const float* K, const float* V, int64_t ld, int64_t B, int32_t T,
+                                      int32_t H, int32_t heads, int64_t row_stride_b, int64_t row_stride_t, const float* bias,
+                                      const float* bias_t, int64_t bias_bstride, const float* ts, int32_t mask_flags, float band,
+                                      const int32_t* allones_flag, const uint8_t* mask, int32_t mask_b, int32_t mask_h,
+                                      const float* ctx, const float* lse, const float* dctx, float* dQ, float* dK, float* dV,
+                                      int64_t ldd, float* dbias, void* workspace, size_t workspace_bytes, tagan_stream_t stream) {
+  if (row_stride_b <= 0 || row_stride_t <= 0) return TAGAN_E_INVALID;
+  return tattn_bwd_impl(Q, K, V, ld, B, T, H, heads, row_stride_b, row_stride_t, bias, bias_t, bias_bstride, ts, mask_flags, band,
+                        allones_flag, mask, mask_b, mask_h, ctx, lse, dctx, dQ, dK, dV, ldd, dbias, workspace, workspace_bytes, stream);
 }
 
 TAGAN_API int tagan_tattn_mask_allones(const float* ts, int64_t B, int32_t T, float band, const uint8_t* mask,

@@ -79,8 +79,15 @@ class GeometricAttention(nn.Module):
         """Stage-level fused path (fused.geo_layer): LayerNorm on, dropout an identity (eval() or p = 0)."""
         return ops.FUSION and self.use_layer_norm and not (self.training and self.dropout_prob > 0)
 
+    def _check_shape(self):
+        if not ops.geo_shape_supported(self.hidden_dim, self.num_heads):
+            raise NotImplementedError(
+                f"geometric attention kernel: hidden_dim={self.hidden_dim} / num_heads={self.num_heads} is not instantiated "
+                "(hidden in {32,64,128,256,512} with a power-of-two head dimension); there is no CPU / eager fallback")
+
     def forward_csr(self, x: torch.Tensor, csr: ops.CSR, return_attention_weights: bool = False):
         """x ``[N,H]`` -> ``[N,H]`` (+ per-entry weights ``[nnz,h]`` aligned with ``csr.row/col``)."""
+        self._check_shape()
         self._warn_attn_dropout()
         if self._fused_ok() and not return_attention_weights:
             return fused.geo_layer(self, x, [csr])
@@ -105,6 +112,7 @@ class GeometricAttention(nn.Module):
         projection, the output projection and LN2 run once over all ``T*N`` rows (one large tcgen05 GEMM each instead
         of T small ones); kernel (a) runs per snapshot on row slices.  Same arithmetic per row as ``forward_csr``."""
         t_steps, n, hdim = x3.shape
+        self._check_shape()
         self._warn_attn_dropout()
         if self._fused_ok():
             return fused.geo_layer(self, x3, csrs)
@@ -218,8 +226,6 @@ class AsymmetricTemporalAttention(nn.Module):
     autograd carries their gradients); LayerNorm, projections and the per-node attention run in
     libtagan_b200.  The reference's data-dependent mask rules are reproduced in ``_resolve_mask``.
     """
-
-    MAX_PER_NODE_BIAS_ELEMS = 1 << 28
 
     def __init__(self, hidden_dim: int, num_heads: int = 8, dropout: float = 0.1, causal: bool = False,
                  time_aware: bool = True, use_layer_norm: bool = True, asymmetric_window_size: int = 5,
@@ -399,6 +405,7 @@ class AsymmetricTemporalAttention(nn.Module):
             qkv = ops.linear(xn, w_qkv, b_qkv)
         bias = self._position_bias(t, dev)
         ts = None
+        per_node = False
         if self.time_aware and time_stamps is not None:
             ts = time_stamps.to(dev).float()
             shared = b == 1 or ts.stride(0) == 0 or bool((ts == ts[0:1]).all())
@@ -406,20 +413,31 @@ class AsymmetricTemporalAttention(nn.Module):
             if shared:
                 bias = bias + self._time_bias(ts[0:1])[0]
             else:
-                nb = self.time_encoding.num_bases
-                if b * t * t * max(nb, self.num_heads) > self.MAX_PER_NODE_BIAS_ELEMS:
-                    raise NotImplementedError("per-node timestamps at this size are not supported yet")
-                bias = bias.unsqueeze(0) + self._time_bias(ts)
+                per_node = True                       # RBF bias per node pair, produced on device chunk by chunk (ops)
         # resolved_mask (extension): the caller already applied the reference's mask rules (e.g. TAGANModel knows its mask is
         # all ones), which skips the host read of `torch.all(mask == 1)` and keeps the call CUDA-graph capturable
         tmask = resolved_mask if resolved_mask is not None else self._resolve_mask(attention_mask, ts, b, t, dev)
-        if use_fused:
+        if per_node:
+            te = self.time_encoding
+            if use_fused:                             # the per-node core is a separate autograd node: unfused layer around it
+                xn = ops.layer_norm(rows, self.layer_norm1.weight, self.layer_norm1.bias) if ln else rows
+                w_qkv = torch.cat([self.q_linear.weight, self.k_linear.weight, self.v_linear.weight], 0)
+                b_qkv = torch.cat([self.q_linear.bias, self.k_linear.bias, self.v_linear.bias], 0)
+                qkv = ops.linear(xn, w_qkv, b_qkv)
+                use_fused = False
+            sigma = torch.clamp(te.basis_sigma, min=1e-7)                         # :173-179
+            wc = self.time_q_proj.weight @ te.basis_proj.weight                   # [h, nb]  (:848: time_k_proj is never used)
+            bc = self.time_q_proj.weight @ te.basis_proj.bias + self.time_q_proj.bias
+            ctx, attn = ops.temporal_attention_core_per_node(qkv, bias, ts, te.basis_mu, sigma, wc, bc, tmask, b, t,
+                                                             self.num_heads, time_major, want_attn=return_attention_weights)
+        elif use_fused:
             out = fused.tattn_layer(self, rows, bias, tmask, b, t, time_major).view(phys.shape)
             if list_input:             # the reference returns a CONTIGUOUS [maxN,T,H] (TAGAN.forward then calls .view on it)
                 return out.permute(1, 0, 2).contiguous()
             return out.permute(1, 0, 2) if time_major else out
-        ctx, attn = ops.temporal_attention_core(qkv, bias, tmask, b, t, self.num_heads, time_major,
-                                                want_attn=return_attention_weights)
+        if not per_node:
+            ctx, attn = ops.temporal_attention_core(qkv, bias, tmask, b, t, self.num_heads, time_major,
+                                                    want_attn=return_attention_weights)
         o = ops.linear(ctx, self.output_proj.weight, self.output_proj.bias)
         o = self.output_dropout(o)
         out = ops.layer_norm(o, self.layer_norm2.weight, self.layer_norm2.bias, res=rows) if ln else ops.add(o, rows)

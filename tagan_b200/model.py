@@ -206,6 +206,7 @@ class TAGANModel(nn.Module):
         skip = x
         for i, layer in enumerate(self.geometric_attention_layers):                                         # :244-262
             ga = layer.geometric_attention
+            ga._check_shape()
             if ga._fused_ok():
                 x = fused.geo_layer(ga, x, csrs)
             else:

@@ -392,6 +392,19 @@ class _GeoAttnFn(torch.autograd.Function):
         return dqkv, dparam, None, None, None, None
 
 
+def geo_shape_supported(hidden: int, heads: int) -> bool:
+    """Shapes kernel (a) is instantiated for (csrc/geo_attn.cu pick_shape): hidden in {32,64,128,256,512} and a power-of-two
+    number of lanes per head -- every named configuration; e.g. 5 heads x 8 is not."""
+    if hidden not in (32, 64, 128, 256, 512) or heads <= 0 or hidden % heads:
+        return False
+    vec = {32: 1, 64: 2}.get(hidden, 4)
+    d = hidden // heads
+    if d % vec:
+        return False
+    group = d // vec
+    return 1 <= group <= 32 and (group & (group - 1)) == 0
+
+
 def geo_attention_core(qkv, csr: CSR, heads: int, metric: str, metric_param=None, want_attn=False):
     """qkv ``[N,3H]`` (fused projection) -> ctx ``[N,H]`` (and per-entry weights ``[cap,h]``)."""
     return _GeoAttnFn.apply(qkv, metric_param, csr, heads, METRIC_ID[metric], want_attn)
@@ -629,6 +642,122 @@ def temporal_attention_core(qkv, bias, tmask: TemporalMask, batch: int, t: int, 
                             time_major: bool = False, want_attn: bool = False):
     """qkv rows ``[B*T,3H]`` -> ctx rows ``[B*T,H]`` (+ ``attn[B,h,T,T]``)."""
     return _TAttnFn.apply(qkv, bias, tmask, batch, t, heads, time_major, want_attn)
+
+
+class _TAttnPerNodeFn(torch.autograd.Function):
+    """Temporal attention core with PER-NODE timestamps: the RBF time bias (reference temporal_attention.py:792-871) is
+    produced on device for a chunk of nodes at a time (``tagan_time_bias_fwd``), consumed by the attention kernel through
+    its per-node bias path and discarded; backward recomputes the tile, takes the chunk's dBias and reduces it to the
+    parameter gradients at once (``tagan_time_bias_bwd``).  No ``[B,T,T,nb]`` or whole-batch ``[B,h,T,T]`` tensor exists."""
+
+    CHUNK_BYTES = 16 << 20          # bias tile per chunk (three such tiles live at once in backward): L2-resident
+
+    @staticmethod
+    def forward(ctx, qkv, pos_bias, ts, mu, sigma, wc, bc, tmask: "TemporalMask", batch: int, t: int, heads: int, time_major: bool,
+                want_attn: bool):
+        lib = _lib.load()
+        qkv2, rows, three_h, ld = _rows(qkv)
+        h = three_h // 3
+        assert rows == batch * t
+        dev = qkv.device
+        nb = mu.numel()
+        ts_c = _f32c(ts).contiguous()
+        ctxv = torch.empty(rows, h, dtype=torch.float32, device=dev)
+        lse = torch.empty(batch, heads, t, dtype=torch.float32, device=dev)
+        attn = torch.empty(batch, heads, t, t, dtype=torch.float32, device=dev) if want_attn else None
+        rng = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.check(lib.tagan_ts_range(_ptr(ts_c), batch, t, _ptr(rng), _stream()), "tagan_ts_range")
+        pos_c = _f32c(pos_bias).contiguous() if pos_bias is not None else None
+        mu_c, sg_c, wc_c, bc_c = (_f32c(v).contiguous() for v in (mu, sigma, wc, bc))
+        htt = heads * t * t
+        chunk = max(1, min(batch, _TAttnPerNodeFn.CHUNK_BYTES // (htt * 4)))
+        bias = torch.empty(chunk, heads, t, t, dtype=torch.float32, device=dev)
+        bias_t = torch.empty_like(bias)
+        rsb, rst = (1, batch) if time_major else (t, 1)
+        m = tmask.mask
+        mb, mh = (m.shape[0], m.shape[1]) if m is not None else (1, 1)
+        base, cbase = qkv2.data_ptr(), ctxv.data_ptr()
+        for b0 in range(0, batch, chunk):
+            bc_n = min(chunk, batch - b0)
+            _lib.check(lib.tagan_time_bias_fwd(_ptr(ts_c), b0, bc_n, t, heads, nb, _ptr(rng), _ptr(mu_c), _ptr(sg_c), _ptr(wc_c),
+                                               _ptr(bc_c), _ptr(pos_c), _ptr(bias), _ptr(bias_t), _stream()), "tagan_time_bias_fwd")
+            off = base + b0 * rsb * ld * 4
+            q, k, v = (C.c_void_p(off + i * h * 4) for i in range(3))
+            mptr = C.c_void_p(m.data_ptr() + b0 * mh * t * t) if (m is not None and mb > 1) else _ptr(m)
+            with _timed("tattn_fwd"):
+                rc = lib.tagan_tattn_fwd_strided(q, k, v, ld, bc_n, t, h, heads, rsb, rst, _ptr(bias), _ptr(bias_t), htt,
+                                                 C.c_void_p(ts_c.data_ptr() + b0 * t * 4), tmask.flags, tmask.band,
+                                                 _ptr(tmask.allones_flag), mptr, mb if mb == 1 else bc_n, mh,
+                                                 C.c_void_p(cbase + b0 * rsb * h * 4), C.c_void_p(lse.data_ptr() + b0 * heads * t * 4),
+                                                 C.c_void_p(attn.data_ptr() + b0 * htt * 4) if attn is not None else None, _stream())
+            _lib.check(rc, "tagan_tattn_fwd_strided")
+            CALLS["n"] += 2
+        ctx.save_for_backward(qkv2, pos_c, ts_c, mu_c, sg_c, wc_c, bc_c, ctxv, lse, rng)
+        ctx.tmask, ctx.dims, ctx.chunk = tmask, (batch, t, heads, time_major, nb), chunk
+        ctx.pos_shape = pos_bias.shape if pos_bias is not None else None
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+        return ctxv, attn
+
+    @staticmethod
+    def backward(ctx, dctx, _dattn):
+        lib = _lib.load()
+        qkv2, pos_c, ts_c, mu_c, sg_c, wc_c, bc_c, ctxv, lse, rng = ctx.saved_tensors
+        tmask = ctx.tmask
+        batch, t, heads, time_major, nb = ctx.dims
+        chunk = ctx.chunk
+        rows, three_h = qkv2.shape
+        h = three_h // 3
+        ld = qkv2.stride(0) if rows > 1 else three_h
+        dev = dctx.device
+        dctx = _f32c(dctx).contiguous()
+        dqkv = torch.empty(rows, three_h, dtype=torch.float32, device=dev)
+        htt = heads * t * t
+        bias = torch.empty(chunk, heads, t, t, dtype=torch.float32, device=dev)
+        bias_t = torch.empty_like(bias)
+        dbias = torch.empty_like(bias)
+        dparams = torch.zeros(heads * nb + heads + 2 * nb, dtype=torch.float32, device=dev)
+        dpos = torch.zeros(heads, t, t, dtype=torch.float32, device=dev) if pos_c is not None else None
+        ws = workspace(lib.tagan_time_bias_bwd_workspace_bytes(heads, nb), dev)
+        rsb, rst = (1, batch) if time_major else (t, 1)
+        m = tmask.mask
+        mb, mh = (m.shape[0], m.shape[1]) if m is not None else (1, 1)
+        base, dbase = qkv2.data_ptr(), dqkv.data_ptr()
+        for b0 in range(0, batch, chunk):
+            bc_n = min(chunk, batch - b0)
+            _lib.check(lib.tagan_time_bias_fwd(_ptr(ts_c), b0, bc_n, t, heads, nb, _ptr(rng), _ptr(mu_c), _ptr(sg_c), _ptr(wc_c),
+                                               _ptr(bc_c), _ptr(pos_c), _ptr(bias), _ptr(bias_t), _stream()), "tagan_time_bias_fwd")
+            off, doff = base + b0 * rsb * ld * 4, dbase + b0 * rsb * three_h * 4
+            q, k, v = (C.c_void_p(off + i * h * 4) for i in range(3))
+            dq, dk, dv = (C.c_void_p(doff + i * h * 4) for i in range(3))
+            mptr = C.c_void_p(m.data_ptr() + b0 * mh * t * t) if (m is not None and mb > 1) else _ptr(m)
+            with _timed("tattn_bwd"):
+                rc = lib.tagan_tattn_bwd_strided(q, k, v, ld, bc_n, t, h, heads, rsb, rst, _ptr(bias), _ptr(bias_t), htt,
+                                                 C.c_void_p(ts_c.data_ptr() + b0 * t * 4), tmask.flags, tmask.band,
+                                                 _ptr(tmask.allones_flag), mptr, mb if mb == 1 else bc_n, mh,
+                                                 C.c_void_p(ctxv.data_ptr() + b0 * rsb * h * 4),
+                                                 C.c_void_p(lse.data_ptr() + b0 * heads * t * 4),
+                                                 C.c_void_p(dctx.data_ptr() + b0 * rsb * h * 4), dq, dk, dv, three_h, _ptr(dbias),
+                                                 None, 0, _stream())
+            _lib.check(rc, "tagan_tattn_bwd_strided")
+            rc = lib.tagan_time_bias_bwd(_ptr(ts_c), b0, bc_n, t, heads, nb, _ptr(rng), _ptr(mu_c), _ptr(sg_c), _ptr(wc_c),
+                                         _ptr(dbias), _ptr(dparams), _ptr(dpos), 1, _ptr(ws), ws.numel(), _stream())
+            _lib.check(rc, "tagan_time_bias_bwd")
+            CALLS["n"] += 5
+        dwc = dparams[:heads * nb].view(heads, nb)
+        dbc = dparams[heads * nb:heads * nb + heads]
+        dmu = dparams[heads * nb + heads:heads * nb + heads + nb]
+        dsg = dparams[heads * nb + heads + nb:]
+        if dpos is not None:
+            dpos = dpos.view(ctx.pos_shape)
+        return dqkv, dpos, None, dmu, dsg, dwc, dbc, None, None, None, None, None, None
+
+
+def temporal_attention_core_per_node(qkv, pos_bias, ts, mu, sigma, wc, bc, tmask: "TemporalMask", batch: int, t: int, heads: int,
+                                     time_major: bool = False, want_attn: bool = False):
+    """qkv rows ``[B*T,3H]`` + per-node timestamps ``ts [B,T]`` -> ctx rows ``[B*T,H]`` (+ ``attn[B,h,T,T]``); the RBF time
+    bias parameters (``mu``, clamped ``sigma`` ``[nb]``, ``wc [h,nb]``, ``bc [h]``) receive their gradients directly."""
+    return _TAttnPerNodeFn.apply(qkv, pos_bias, ts, mu, sigma, wc, bc, tmask, batch, t, heads, time_major, want_attn)
 
 
 # ----------------------------------------------------------------------------------------
