@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--e2e-no-prefetch", action="store_true",
                     help="e2e arm: H2D copies inside the step's graph instead of prefetching the next step's inputs")
     ap.add_argument("--no-bank", action="store_true")
+    ap.add_argument("--c5-nodes", type=int, default=25_000, help="node count of the config-5 sample (T stays 128)")
     ap.add_argument("--no-partitioned", action="store_true",
                     help="N >= 2: skip the node-partitioned config-4 block that follows the data-parallel measurement")
     ap.add_argument("--cuda-profiler", action="store_true",
@@ -92,7 +93,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "c1":
+        print(json.dumps({"impl": "reference", "unavailable": "config 1 is the whole-model case; the CPU arm of this bench times the "
+                          "layer-level oracle port only (the reference's own TAGAN on config 1, timed in the build container, is in "
+                          "profiles/r02_reference_cpu_c1_c2.json)"}), flush=True)
+        return
     w = synth.WORKLOADS[args.workload]
+    if args.workload == "c5":
+        import dataclasses
+        w = dataclasses.replace(w, num_nodes=args.c5_nodes, num_edges=int(w.num_edges * args.c5_nodes / w.num_nodes),
+                                name=w.name + f" (node sample: {args.c5_nodes} of {w.num_nodes} nodes, same average degree)")
     step, units, desc = cpu_sample_step_factory(w, args.metric)
     for _ in range(min(args.warmup, 1)):          # CPU path: one warm-up is enough to fault pages in
         step()
@@ -319,6 +329,87 @@ def run_partitioned(w, metric, world, rank, dev, steps, warmup, no_bank=False, w
     return res
 
 
+# ------------------------------------------------------------------------------------------
+# config 1: the reference's own example.py case -- the WHOLE model (TAGAN.forward + loss + backward + clip + Adam)
+# ------------------------------------------------------------------------------------------
+def example_sequence(seed=0):
+    """example.py:23-65: T = 5 snapshots of 5..10 nodes, 16 node features, 2 N_t edges, 8 edge features."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    g = torch.Generator().manual_seed(seed)
+    seq = []
+    for _ in range(5):
+        nt = int(rng.randint(5, 11))
+        seq.append((torch.randn(nt, 16, generator=g), torch.randint(0, nt, (2, 2 * nt), generator=g), torch.randn(2 * nt, 8, generator=g),
+                    rng.choice(10, nt, replace=False).tolist()))
+    return seq
+
+
+def run_c1(args, rank, world, dev):
+    """One training step of the whole model on the example.py shapes (example.py:131-159: hidden 64, 4 heads, 2 layers,
+    output_dim 1, BCE), captured as one CUDA graph (tagan_b200.head.TrainStep).  Units = raw edges of the sequence."""
+    import tagan_b200
+    from tagan_b200 import ops
+    from tagan_b200.head import TrainStep
+    cfg = dict(node_feature_dim=16, edge_feature_dim=8, hidden_dim=64, num_heads=4, num_layers=2, output_dim=1, dropout=0.0,
+               loss_type="bce", use_edge_features=True, learnable_distance=False, temporal_window_size=3)
+    seq = example_sequence(rank)
+    units = sum(int(s[1].shape[1]) for s in seq)
+    torch.manual_seed(0)
+    model = tagan_b200.TAGANModel(cfg).to(dev).eval()
+    opt = tagan_b200.FusedAdam(list(model.parameters()), lr=1e-3, max_grad_norm=1.0)
+    host = tagan_b200.PackedSequence.from_snapshots([s[0] for s in seq], [s[1] for s in seq], pin=True)
+    packed = host.to(dev)
+    labels = torch.tensor([[1.0]], device=dev)
+    step = TrainStep(model, opt)
+    ops.CALLS["n"] = 0
+    step.eager(packed, labels)
+    launches = ops.CALLS["n"]
+    step.capture(packed, labels)
+    for _ in range(max(args.warmup, 3)):
+        step.replay()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step.replay()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    # e2e: the packed sequence starts in pinned host memory every step (4 copies), the loss is read back
+    loss_h = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        for d, h in ((packed.x, host.x), (packed.edges, host.edges)):
+            d.copy_(h, non_blocking=True)
+        loss_h.copy_(step.replay(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_h)
+    e2e_step()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        last = e2e_step()
+    g1.record()
+    torch.cuda.synchronize()
+    ems = g0.elapsed_time(g1) / args.steps
+    return {"metric": METRIC, "value": units * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c1-example-toy (whole model: TAGAN.forward + BCE + backward + clip_grad_norm + Adam)",
+                       "snapshots": 5, "nodes": [int(s[0].shape[0]) for s in seq], "edges_per_sequence": units, "hidden": 64,
+                       "heads": 4, "layers": 2, "parallelism": f"dp{world}", "l2": "working set of a few hundred KB: launch-latency "
+                       "bound, L2-resident by construction (the reference's own CPU-runnable case)",
+                       "timing": "one CUDA graph replay per step"},
+            "roofline": {"bound": "launch latency (tiny tensors)", "achieved": None, "peak": None, "unit": "GB/s", "frac": None,
+                         "traffic": None, "kernels_per_step": launches},
+            "cpu_baseline": None,
+            "e2e": {"value": units * world / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "h2d_bytes_per_step": host.x.numel() * 4 +
+                    host.edges.numel() * 8, "d2h_bytes_per_step": 4, "loss": last,
+                    "mode": "pinned packed sequence -> 2 H2D copies -> graph replay (fwd + loss + bwd + clip + Adam) -> loss D2H"},
+            "gpu_launches": launches * args.steps}
+
+
 def run_ours(args):
     import torch.distributed as dist
     import tagan_b200
@@ -333,7 +424,23 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "c1":
+        line = run_c1(args, rank, world, dev)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     w = synth.WORKLOADS[args.workload]
+    if args.workload == "c5":
+        # long horizon (T = 128): [T,N,H] activations of the full 250k-node graph are 16 GB each, the layer keeps ~35 of them
+        # for backward -- run the largest node count that fits (same degree, same T) and say so
+        import dataclasses
+        full_n = w.num_nodes
+        n_fit = args.c5_nodes
+        w = dataclasses.replace(w, num_nodes=n_fit, num_edges=int(w.num_edges * n_fit / full_n),
+                                name=w.name + f" (node sample: {n_fit} of {full_n} nodes, same average degree)")
     if args.workload == "c4":
         # the north-star configuration: ONE graph of 1M nodes, node-partitioned (does not fit one GPU at T=16: runs the
         # largest snapshot count that does, and says so)

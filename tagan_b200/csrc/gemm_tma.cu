@@ -142,6 +142,8 @@ struct Params {
   int b_presplit;          // B arrives already split (tmB = hi image, tmB2 = lo image): only A is split in-kernel
   uint32_t idesc;
   float* colsum_part;       // TN only: [splits][2][M] partial column sums of A (the bias gradient), or null
+  int cta_acc;              // split-K: every CTA accumulates its splits into ITS OWN partial tile (read-modify-write, fp32
+                            // round-to-nearest) instead of one partial tile per split
   int fused;                // the epilogue is epi (a tagan_epilogue mode), not the plain store through C
   int64_t K1;               // > 0: A is the column concatenation [A (k < K1) | A2 (k >= K1)] (tmA / tmA2), NT only
   tagan_epilogue epi;       // fused epilogue (mode 0 = plain store / bias / accumulate through C)
@@ -611,10 +613,11 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      float* out = p.partial ? p.partial + (int64_t)ks * p.M * p.N : p.C;
+      float* out = p.partial ? p.partial + (int64_t)(p.cta_acc ? (int)blockIdx.x : ks) * p.M * p.N : p.C;
       const int64_t ldo = p.partial ? p.N : p.ldc;
       const bool interior = p.c_vec && ((int64_t)(mt + 1) * BM <= p.M) && (n0 + BN <= p.N);
-      const bool rmw = p.partial == nullptr && p.accumulate;                  // C += A.B (the GRU scan's per-step GEMMs)
+      // C += A.B (the GRU scan's per-step GEMMs), or this CTA's partial tile += its next split
+      const bool rmw = p.partial == nullptr ? (p.accumulate != 0) : (p.cta_acc != 0);
       const bool bias_vec = p.partial == nullptr && p.bias != nullptr;       // host guarantees 16-byte alignment when c_vec
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
@@ -668,6 +671,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           }
         } else {
           const bool direct = p.partial == nullptr;
+          const bool acc_here = direct ? (p.accumulate != 0) : (p.cta_acc != 0);
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (direct && p.bias) {
             if (c0 < p.N) b4.x = p.bias[c0];
@@ -684,7 +688,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
             float* orow = out + grow * ldo + c0;
             if (c0 + 3 < p.N && p.c_vec) {
-              if (direct && p.accumulate) {
+              if (acc_here) {
                 float4 o4 = *reinterpret_cast<const float4*>(orow);
                 v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
               }
@@ -693,7 +697,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
               const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                if (c0 + q < p.N) orow[q] = (direct && p.accumulate) ? orow[q] + vv[q] : vv[q];
+                if (c0 + q < p.N) orow[q] = acc_here ? orow[q] + vv[q] : vv[q];
             }
           }
         }
@@ -713,28 +717,69 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
   }
 }
 
-__global__ void tma_splitk_reduce(const float* __restrict__ partial, int parts, int64_t M, int64_t N,
-                                 const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * N) return;
-  float s = 0.f;
-  for (int q = 0; q < parts; ++q) s += partial[(int64_t)q * M * N + i];
-  const int64_t m = i / N, n = i - m * N;
-  if (bias) s += bias[n];
-  float* o = C + m * ldc + n;
-  *o = accumulate ? *o + s : s;
+// C (+)= sum over `parts` partial tiles (+ bias).  Up to ~1600 parts: a block takes 32 consecutive elements x 8 interleaved
+// slices of the parts, four independent accumulators per thread (loads in flight), then the slices in order -- a fixed
+// summation order (deterministic) with enough parallelism that the reduction streams instead of chasing latency.
+__global__ void __launch_bounds__(256)
+tma_splitk_reduce(const float* __restrict__ partial, int parts, int64_t M, int64_t N,
+                  const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate) {
+  __shared__ float red[8][32];
+  const int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int slice = threadIdx.x >> 5;
+  const int64_t MN = M * N;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (i < MN) {
+    int q = slice;
+    for (; q + 24 < parts; q += 32) {
+      a0 += partial[(int64_t)q * MN + i];
+      a1 += partial[(int64_t)(q + 8) * MN + i];
+      a2 += partial[(int64_t)(q + 16) * MN + i];
+      a3 += partial[(int64_t)(q + 24) * MN + i];
+    }
+    for (; q < parts; q += 8) a0 += partial[(int64_t)q * MN + i];
+  }
+  red[slice][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (slice == 0 && i < MN) {
+    float s = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][threadIdx.x];
+    const int64_t m = i / N, n = i - m * N;
+    if (bias) s += bias[n];
+    float* o = C + m * ldc + n;
+    *o = accumulate ? *o + s : s;
+  }
 }
 
-// out[m] = sum over the [parts] partial rows in ascending order (fixed => deterministic)
-__global__ void colsum_parts_reduce(const float* __restrict__ part, int parts, int64_t M, float* __restrict__ out) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  float s = 0.f;
-  for (int j = 0; j < parts; ++j) s += part[(int64_t)j * M + m];
-  out[m] = s;
+// out[m] = sum over the [parts] partial rows: 32 columns x 8 interleaved slices per block, slices combined in order
+// (fixed => deterministic); same shape as tma_splitk_reduce so thousands of parts stream instead of chasing latency
+__global__ void __launch_bounds__(256)
+colsum_parts_reduce(const float* __restrict__ part, int parts, int64_t M, float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int64_t m = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int slice = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (m < M) {
+    int q = slice;
+    for (; q + 24 < parts; q += 32) {
+      a0 += part[(int64_t)q * M + m];
+      a1 += part[(int64_t)(q + 8) * M + m];
+      a2 += part[(int64_t)(q + 16) * M + m];
+      a3 += part[(int64_t)(q + 24) * M + m];
+    }
+    for (; q < parts; q += 8) a0 += part[(int64_t)q * M + m];
+  }
+  red[slice][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (slice == 0 && m < M) {
+    float s = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][threadIdx.x];
+    out[m] = s;
+  }
 }
 
-struct Plan { int tiles_m, tiles_n, splits; int64_t k_per_split; };
+struct Plan { int tiles_m, tiles_n, splits, cta_acc, parts; int64_t k_per_split; };
 Plan make_plan(int64_t M, int64_t N, int64_t K) {
   Plan pl;
   pl.tiles_m = (int)((M + BM - 1) / BM);
@@ -747,12 +792,25 @@ Plan make_plan(int64_t M, int64_t N, int64_t K) {
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
   }
+  pl.cta_acc = 0;
+  if (K >= 65536) {
+    // Long reductions (the dW GEMMs: K = T*N rows).  tcgen05 accumulates in TMEM with round-toward-zero, a bias that grows
+    // linearly with the number of sequential k-steps (measured: 1e-4 of the gradient's magnitude at 5400 rows per split, K = 1.6M).
+    // Keep every TMEM accumulation to ~1024 rows; each CTA adds its splits into its own partial tile in fp32 round-to-nearest
+    // (an L2-resident read-modify-write), and the <= 148 CTA tiles are reduced in a fixed order.
+    const int64_t want = K / 1024;
+    if (want > splits) splits = want;
+    pl.cta_acc = 1;
+  }
   int64_t kps = (K + splits - 1) / splits;
   kps = (kps + BK - 1) / BK * BK;
   if (kps < BK) kps = BK;
   pl.k_per_split = kps;
   pl.splits = (int)((K + kps - 1) / kps);
   if (pl.splits < 1) pl.splits = 1;
+  if (pl.splits == 1) pl.cta_acc = 0;
+  const int64_t work = tiles * pl.splits;
+  pl.parts = pl.cta_acc ? (int)(work < 148 ? work : 148) : pl.splits;
   return pl;
 }
 
@@ -825,7 +883,7 @@ size_t tagan_gemm_tma_colsum_bytes(int64_t M, int64_t N, int64_t K) {
 
 size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K) {
   Plan pl = make_plan(M, N, K);
-  size_t b = pl.splits > 1 ? (size_t)pl.splits * (size_t)M * (size_t)N * sizeof(float) : 0;
+  size_t b = pl.splits > 1 ? (size_t)pl.parts * (size_t)M * (size_t)N * sizeof(float) : 0;
   if (want_presplit(op, N, K)) {
     const int64_t rows = op == 0 ? N : K, cols = op == 0 ? K : N;
     b = (b + 255) / 256 * 256 + 2 * (size_t)rows * presplit_ld(cols) * sizeof(float) + 256;
@@ -869,14 +927,19 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   p.b_mn_major = (op != 0);
   p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.splits = pl.splits; p.k_per_split = pl.k_per_split;
   p.partial = nullptr;
+  p.cta_acc = pl.cta_acc;
   if (pl.splits > 1) {
-    if (!workspace || workspace_bytes < (size_t)pl.splits * M * N * sizeof(float)) return TAGAN_E_WORKSPACE;
+    if (!workspace || workspace_bytes < (size_t)pl.parts * M * N * sizeof(float)) return TAGAN_E_WORKSPACE;
     p.partial = static_cast<float*>(workspace);
+    if (pl.cta_acc) {
+      cudaError_t me = cudaMemsetAsync(p.partial, 0, (size_t)pl.parts * M * N * sizeof(float), st);
+      if (me != cudaSuccess) return (int)me;
+    }
   }
   p.colsum_part = nullptr;
   if (colsum_a != nullptr) {
     if (op != 2) return TAGAN_E_INVALID;
-    const size_t off = pl.splits > 1 ? ((size_t)pl.splits * M * N * sizeof(float) + 255) / 256 * 256 : 0;
+    const size_t off = pl.splits > 1 ? ((size_t)pl.parts * M * N * sizeof(float) + 255) / 256 * 256 : 0;
     if (!workspace || workspace_bytes < off + 2 * (size_t)pl.splits * M * sizeof(float)) return TAGAN_E_WORKSPACE;
     p.colsum_part = reinterpret_cast<float*>(static_cast<char*>(workspace) + off);
   }
@@ -894,7 +957,7 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   bool okB;
   if (want_presplit(op, N, K) && passes != 1) {
     const int64_t rows = op == 0 ? N : K, cols = op == 0 ? K : N, ldo = presplit_ld(cols);
-    size_t off = pl.splits > 1 ? ((size_t)pl.splits * M * N * sizeof(float) + 255) / 256 * 256 : 0;
+    size_t off = pl.splits > 1 ? ((size_t)pl.parts * M * N * sizeof(float) + 255) / 256 * 256 : 0;
     if (!workspace || workspace_bytes < off + 2 * (size_t)rows * ldo * sizeof(float)) return TAGAN_E_WORKSPACE;
     float* hi = reinterpret_cast<float*>(static_cast<char*>(workspace) + off);
     float* lo = hi + rows * ldo;
@@ -911,8 +974,8 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   int grid = (int)(work < 148 ? work : 148);
   gemm_tma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
   if (p.partial)
-    tma_splitk_reduce<<<ceil_div_i64(M * N, 256), 256, 0, st>>>(p.partial, pl.splits, M, N, bias, C, ldc, accumulate);
+    tma_splitk_reduce<<<ceil_div_i64(M * N, 32), 256, 0, st>>>(p.partial, pl.parts, M, N, bias, C, ldc, accumulate);
   if (p.colsum_part)
-    colsum_parts_reduce<<<ceil_div_i64(M, 256), 256, 0, st>>>(p.colsum_part, 2 * pl.splits, M, colsum_a);
+    colsum_parts_reduce<<<ceil_div_i64(M, 32), 256, 0, st>>>(p.colsum_part, 2 * pl.splits, M, colsum_a);
   return tagan_launch_status();
 }
