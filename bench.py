@@ -204,7 +204,7 @@ def run_partitioned(w, metric, world, rank, dev, steps, warmup, no_bank=False, w
     import torch.distributed as dist
     import tagan_b200
     from tagan_b200 import fused, ops, partitioned
-    from tagan_b200.dist import GradBucket, NodePartition
+    from tagan_b200.dist import FlatGradBucket, NodePartition
     n, e, hdim, heads = w.num_nodes, w.num_edges, w.hidden, w.heads
     t_steps = partitioned_snapshots(w, world)
     t_loc = t_steps // world
@@ -246,10 +246,10 @@ def run_partitioned(w, metric, world, rank, dev, steps, warmup, no_bank=False, w
     if not no_bank:
         bank = tagan_b200.NodeMemoryBank(hdim, 0.8, 3, device=dev, capacity=n_loc)
         bank.check_range = False
-    bucket = GradBucket(list(layer.parameters())) if world > 1 else None
+    bucket = FlatGradBucket(list(layer.parameters()))
 
     def step(x, eis):
-        layer.zero_grad(set_to_none=True)
+        bucket.zero()
         out = partitioned.forward_snapshot_parallel(layer, x, eis, part, rank, comm, ts_loc, bank)
         loss = fused.mean_square(out.permute(1, 0, 2))
         loss.backward()
@@ -484,11 +484,12 @@ def run_ours(args):
     if not args.no_bank:
         bank = tagan_b200.NodeMemoryBank(hdim, 0.8, 3, device=dev, capacity=n)
         bank.check_range = False
-    from tagan_b200.dist import GradBucket
-    bucket = GradBucket(list(layer.parameters())) if world > 1 else None
+    from tagan_b200.dist import FlatGradBucket
+    # every p.grad is a view of one flat buffer: backward accumulates in place, the all-reduce needs no packing
+    bucket = FlatGradBucket(list(layer.parameters()))
 
     def fwd_bwd(xs, eis):
-        layer.zero_grad(set_to_none=True)
+        bucket.zero()
         out = layer(xs, eis, ts_d, bank=bank, node_ids=[ids] * t_steps)       # [N,T,H] view of time-major storage
         # mean of squares, taken in the storage order of `out` (a permutation of the same elements) so that the
         # loss and its gradient are contiguous element-wise passes instead of strided ones

@@ -751,30 +751,30 @@ tma_splitk_reduce(const float* __restrict__ partial, int parts, int64_t M, int64
   }
 }
 
-// out[m] = sum over the [parts] partial rows: 32 columns x 8 interleaved slices per block, slices combined in order
-// (fixed => deterministic); same shape as tma_splitk_reduce so thousands of parts stream instead of chasing latency
-__global__ void __launch_bounds__(256)
+// out[m] = sum over the [parts] partial rows: 32 columns x 32 interleaved slices per block (M is only 128..768 wide, so
+// the parallelism has to come from the parts: up to ~3000 of them), slices combined in order (fixed => deterministic)
+__global__ void __launch_bounds__(1024)
 colsum_parts_reduce(const float* __restrict__ part, int parts, int64_t M, float* __restrict__ out) {
-  __shared__ float red[8][32];
+  __shared__ float red[32][32];
   const int64_t m = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
   const int slice = threadIdx.x >> 5;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (m < M) {
     int q = slice;
-    for (; q + 24 < parts; q += 32) {
+    for (; q + 96 < parts; q += 128) {
       a0 += part[(int64_t)q * M + m];
-      a1 += part[(int64_t)(q + 8) * M + m];
-      a2 += part[(int64_t)(q + 16) * M + m];
-      a3 += part[(int64_t)(q + 24) * M + m];
+      a1 += part[(int64_t)(q + 32) * M + m];
+      a2 += part[(int64_t)(q + 64) * M + m];
+      a3 += part[(int64_t)(q + 96) * M + m];
     }
-    for (; q < parts; q += 8) a0 += part[(int64_t)q * M + m];
+    for (; q < parts; q += 32) a0 += part[(int64_t)q * M + m];
   }
   red[slice][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (slice == 0 && m < M) {
     float s = red[0][threadIdx.x];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) s += red[k][threadIdx.x];
+    for (int k = 1; k < 32; ++k) s += red[k][threadIdx.x];
     out[m] = s;
   }
 }
@@ -976,6 +976,6 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   if (p.partial)
     tma_splitk_reduce<<<ceil_div_i64(M * N, 32), 256, 0, st>>>(p.partial, pl.parts, M, N, bias, C, ldc, accumulate);
   if (p.colsum_part)
-    colsum_parts_reduce<<<ceil_div_i64(M, 32), 256, 0, st>>>(p.colsum_part, 2 * pl.splits, M, colsum_a);
+    colsum_parts_reduce<<<ceil_div_i64(M, 32), 1024, 0, st>>>(p.colsum_part, 2 * pl.splits, M, colsum_a);
   return tagan_launch_status();
 }

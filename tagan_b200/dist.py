@@ -49,6 +49,33 @@ class GradBucket:
                 p.grad.copy_(g)
 
 
+class FlatGradBucket:
+    """Data-parallel gradient bucket WITHOUT per-parameter copies: every ``p.grad`` is a view into one flat fp32 buffer
+    (autograd accumulates into the views in place), so the all-reduce is ONE collective on ``flat`` and nothing is packed
+    or unpacked.  Use ``bucket.zero()`` instead of ``zero_grad(set_to_none=True)`` (which would drop the views)."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            p.grad = self.flat[off:off + k].view_as(p)
+            off += (k + 3) // 4 * 4
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self, world: int):
+        """Mean over ranks, in place; the parameters' ``.grad`` views see the result immediately."""
+        if world > 1:
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat.div_(world)
+
+
 @dataclass
 class NodePartition:
     """Contiguous 1-D partition of node ids ``0..N-1`` over ``world`` ranks (equal blocks, the last

@@ -43,6 +43,18 @@ def _worker(rank, world, port, q):
     dist.all_gather(outs, pad)
     full = torch.cat([o[:s] for o, s in zip(outs, part.sizes())])
     ok = ok and torch.equal(full[:, 0], torch.arange(11, dtype=torch.float32))
+    # flat-view bucket: grads accumulate into one buffer, one all-reduce, no copies
+    from tagan_b200.dist import FlatGradBucket
+    lin2 = torch.nn.Linear(5, 3)
+    with torch.no_grad():
+        for p_, q_ in zip(lin2.parameters(), lin.parameters()):
+            p_.copy_(q_)
+    fb = FlatGradBucket(list(lin2.parameters()))
+    fb.zero()
+    lin2(x).sum().backward()
+    assert all(p_.grad.untyped_storage().data_ptr() == fb.flat.untyped_storage().data_ptr() for p_ in lin2.parameters())
+    fb.all_reduce(world)
+    ok = ok and all(torch.allclose(p_.grad, q_.grad) for p_, q_ in zip(lin2.parameters(), lin.parameters()))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
