@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--e2e-no-prefetch", action="store_true",
                     help="e2e arm: H2D copies inside the step's graph instead of prefetching the next step's inputs")
     ap.add_argument("--no-bank", action="store_true")
+    ap.add_argument("--qkv-storage", default="fp32", choices=["fp32", "bf16"],
+                    help="bf16: the geometric layer stores its projected q/k/v rows in bf16 (fp32 arithmetic; separate tolerance)")
     ap.add_argument("--c5-nodes", type=int, default=25_000, help="node count of the config-5 sample (T stays 128)")
     ap.add_argument("--no-partitioned", action="store_true",
                     help="N >= 2: skip the node-partitioned config-4 block that follows the data-parallel measurement")
@@ -198,7 +200,7 @@ def partitioned_snapshots(w, world):
     return world
 
 
-def run_partitioned(w, metric, world, rank, dev, steps, warmup, no_bank=False, want_e2e=True):
+def run_partitioned(w, metric, world, rank, dev, steps, warmup, no_bank=False, want_e2e=True, qkv_storage="fp32"):
     """One TAGAN layer fwd+bwd on ONE graph of w.num_nodes nodes over `world` GPUs (tagan_b200.partitioned.
     forward_snapshot_parallel).  Inputs are generated on the device (16 GB of host randn would dominate the run)."""
     import torch.distributed as dist
@@ -235,6 +237,7 @@ def run_partitioned(w, metric, world, rank, dev, steps, warmup, no_bank=False, w
     torch.manual_seed(0)
     layer = tagan_b200.TAGANLayer(hdim, heads, metric).to(dev)
     layer.geometric.validate_indices = False
+    layer.geometric.geometric_attention.qkv_storage = qkv_storage
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     x_loc = torch.randn(t_steps, n_loc, hdim, device=dev, generator=gen)
     my_eis = []
@@ -447,12 +450,15 @@ def run_ours(args):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        res = run_partitioned(w, args.metric, world, rank, dev, args.steps, args.warmup, args.no_bank, not args.no_e2e)
+        res = run_partitioned(w, args.metric, world, rank, dev, args.steps, args.warmup, args.no_bank, not args.no_e2e,
+                              args.qkv_storage)
         clocks = sampler.stop() if rank == 0 else None
         if rank == 0:
             line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                     "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-                    "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (generated on device)",
+                    "scaling": "strong", "vs_baseline": None,
+                    "dtype": "f32" if args.qkv_storage == "fp32" else "f32 arithmetic, q/k/v rows stored bf16",
+                    "data": "synthetic (generated on device)",
                     "config": {"workload": w.name, "nodes": res["nodes"], "edges_per_snapshot": res["edges_per_snapshot"],
                                "snapshots": res["snapshots"], "snapshots_of": res["snapshots_of"], "hidden": res["hidden"],
                                "heads": res["heads"], "distance_metric": args.metric, "parallelism": res["mode"],
@@ -480,6 +486,7 @@ def run_ours(args):
     ids = torch.arange(n, dtype=torch.int32, device=dev)
     torch.manual_seed(0)
     layer = tagan_b200.TAGANLayer(hdim, w.heads, args.metric).to(dev)
+    layer.geometric.geometric_attention.qkv_storage = args.qkv_storage
     bank = None
     if not args.no_bank:
         bank = tagan_b200.NodeMemoryBank(hdim, 0.8, 3, device=dev, capacity=n)
@@ -734,7 +741,8 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f32" if args.qkv_storage == "fp32" else "f32 arithmetic, q/k/v rows stored bf16",
+                "data": "synthetic",
                 "config": {"workload": w.name, "nodes": n, "edges_per_snapshot": e, "snapshots": t_steps,
                            "hidden": hdim, "heads": h, "distance_metric": args.metric,
                            "parallelism": f"dp{world} (one sequence per GPU, NCCL grad all-reduce)",

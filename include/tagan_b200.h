@@ -174,6 +174,29 @@ int tagan_gemm_tn_colsum(int64_t m, int64_t n, int64_t k, const float* A, int64_
                          float* C, int64_t ldc, float* colsum_a, int32_t precision,
                          void* workspace, size_t workspace_bytes, tagan_stream_t stream);
 
+/* bf16-STORAGE variants of kernel (a) (north_star: "bf16 tolerances stated separately"): Q, K, V rows are bf16 (raw 16-bit
+ * words, leading dimension in elements), which halves the gather traffic; scores, softmax, aggregation and every gradient
+ * are computed and returned in fp32.  Same arguments otherwise.  Parity: against the reference arithmetic with q, k, v rounded
+ * to bf16 (round-to-nearest-even) at the fp32 tolerance; against the fp32 reference itself at rtol 2e-2 / atol 2e-2. */
+int tagan_geo_attn_fwd_bf16(const uint16_t* Q, const uint16_t* K, const uint16_t* V, int64_t ld, const int32_t* rowptr,
+                            const int32_t* col, int32_t N, int32_t H, int32_t heads, int32_t metric,
+                            const float* metric_param, float* ctx, float* lse, float* attn, tagan_stream_t stream);
+int tagan_geo_attn_bwd_bf16(const uint16_t* Q, const uint16_t* K, const uint16_t* V, int64_t ld, const int32_t* rowptr,
+                            const int32_t* col, const int32_t* rowptr_t, const int32_t* row_t, int32_t N, int32_t H,
+                            int32_t heads, int32_t metric, const float* metric_param, const float* ctx, const float* lse,
+                            const float* dctx, float* dQ, float* dK, float* dV, int64_t ldd, float* delta_ws,
+                            float* dparam_ws, float* dparam, tagan_stream_t stream);
+int tagan_geo_attn_fwd_part_bf16(const uint16_t* Q, int64_t ldq, const uint16_t* K, const uint16_t* V, int64_t ldkv,
+                                 const int32_t* rowptr, const int32_t* col, int32_t n_rows, int32_t H, int32_t heads,
+                                 int32_t metric, const float* metric_param, float* ctx, float* lse, float* attn,
+                                 tagan_stream_t stream);
+int tagan_geo_attn_bwd_part_bf16(const uint16_t* Q, int64_t ldq, const uint16_t* K, const uint16_t* V, int64_t ldkv,
+                                 const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* row_t,
+                                 int32_t n_rows, int32_t n_src, int32_t H, int32_t heads, int32_t metric,
+                                 const float* metric_param, const float* ctx, const float* lse, const float* dctx,
+                                 float* dQ, int64_t lddq, float* dK, float* dV, int64_t lddkv, float* delta_ws,
+                                 float* dparam_ws, float* dparam, tagan_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Projections with the reference's surrounding element-wise / LayerNorm code fused into the GEMM
  * (SURVEY.md section 8b "tagan_gemm_ln_qkv / tagan_gemm_out_res_ln / tagan_gru_epilogue_*"): the
@@ -203,7 +226,8 @@ enum tagan_epi_mode {
   TAGAN_EPI_RES_LN = 1,
   TAGAN_EPI_GATES = 2,
   TAGAN_EPI_BLEND = 3,
-  TAGAN_EPI_GATES_BWD = 4
+  TAGAN_EPI_GATES_BWD = 4,
+  TAGAN_EPI_STORE_BF16 = 5 /* out0 is a bf16 matrix (raw 16-bit words, ld_out0 in elements): acc + bias, round-to-nearest-even */
 };
 struct tagan_epilogue {
   int32_t mode;

@@ -137,7 +137,7 @@ def segment_softmax_aggregate(s, v_col, row, num_rows):
 def geo_attention(x: torch.Tensor, sd: Dict[str, torch.Tensor], edge_index, num_heads: int,
                   metric: str = "scaled_dot_product", use_layer_norm: bool = True,
                   learnable_distance: bool = False, csr: Optional[dict] = None,
-                  return_attn: bool = False):
+                  return_attn: bool = False, qkv_round: Optional[torch.dtype] = None):
     """``TAGANGraphAttention.forward`` (graph_attention.py:61-133) ->
     ``GeometricAttention.forward`` (geometric_attention.py:518-598) on the entry set of
     :func:`build_csr`.  ``sd`` keys: ``{q,k,v}_linear.*, output_proj.*, layer_norm{1,2}.*``
@@ -154,6 +154,11 @@ def geo_attention(x: torch.Tensor, sd: Dict[str, torch.Tensor], edge_index, num_
     q = _lin(xn, sd, "q_linear").view(n, num_heads, d)                   # :546-560
     k = _lin(xn, sd, "k_linear").view(n, num_heads, d)
     v = _lin(xn, sd, "v_linear").view(n, num_heads, d)
+    if qkv_round is not None:
+        # restatement of the bf16-STORAGE mode of the product (not a reference feature): q, k, v are rounded to `qkv_round`
+        # (round-to-nearest-even) where they are stored, everything else stays in the working precision; the rounding is a
+        # straight-through op for the gradient, as in the product
+        q, k, v = (t + (t.to(qkv_round).to(t.dtype) - t).detach() for t in (q, k, v))
     param = sd.get("distance_param") if (learnable_distance and metric in ("gaussian_kernel", "rbf_kernel")) else None
     s = edge_scores(q[row], k[col], metric, param)                       # :332-503
     a, ctx = segment_softmax_aggregate(s, v[col], row, n)                # :505-511, :579

@@ -24,7 +24,7 @@ class Epilogue(C.Structure):
                 ("gamma", _p), ("beta", _p), ("mean", _p), ("rstd", _p)]
 
 
-EPI_STORE, EPI_RES_LN, EPI_GATES, EPI_BLEND, EPI_GATES_BWD = range(5)
+EPI_STORE, EPI_RES_LN, EPI_GATES, EPI_BLEND, EPI_GATES_BWD, EPI_STORE_BF16 = range(6)
 
 
 class HeadWeights(C.Structure):
@@ -50,6 +50,12 @@ SIGNATURES = {
     "tagan_geo_attn_fwd": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "tagan_geo_attn_bwd": (_i32, [_p, _p, _p, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
                                   _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "tagan_geo_attn_fwd_bf16": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "tagan_geo_attn_bwd_bf16": (_i32, [_p, _p, _p, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
+                                       _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "tagan_geo_attn_fwd_part_bf16": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "tagan_geo_attn_bwd_part_bf16": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
+                                            _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p]),
     "tagan_layernorm_fwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i32, _p]),
     "tagan_layernorm_bwd_workspace_bytes": (_sz, [_i64, _i32]),
     "tagan_layernorm_bwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _sz,

@@ -26,7 +26,9 @@ def _sources():
 
 def _digest(path):
     h = hashlib.sha1()
-    for dep in [path] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
+    includes_cu = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
+                   if f.endswith(".cu") and ('#include "%s"' % f) in open(path).read()]      # e.g. geo_attn_bf16.cu
+    for dep in [path] + includes_cu + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
             [os.path.join(os.path.dirname(HERE), "include", "tagan_b200.h")]:
         with open(dep, "rb") as fh:
             h.update(fh.read())

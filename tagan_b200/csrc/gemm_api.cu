@@ -98,8 +98,9 @@ TAGAN_API int tagan_gemm_fused(int32_t op, int64_t m, int64_t n, int64_t k, cons
   if (precision < 1 || precision > 3) return TAGAN_E_INVALID;
   if (m == 0) return 0;
   const tagan_epilogue& e = *epi;
-  if (e.mode < TAGAN_EPI_STORE || e.mode > TAGAN_EPI_GATES_BWD) return TAGAN_E_INVALID;
-  if (n % 4 || !al16p(bias) || !al16p(e.out0) || e.ld_out0 % 4) return TAGAN_E_UNSUPPORTED;
+  if (e.mode < TAGAN_EPI_STORE || e.mode > TAGAN_EPI_STORE_BF16) return TAGAN_E_INVALID;
+  if (n % 4 || !al16p(bias) || e.ld_out0 % 4) return TAGAN_E_UNSUPPORTED;
+  if (e.mode == TAGAN_EPI_STORE_BF16 ? (reinterpret_cast<uintptr_t>(e.out0) & 7) != 0 : !al16p(e.out0)) return TAGAN_E_UNSUPPORTED;
   if ((e.in0 && (!al16p(e.in0) || e.ld_in0 % 4)) || (e.in1 && (!al16p(e.in1) || e.ld_in1 % 4)) ||
       (e.out1 && (!al16p(e.out1) || e.ld_out1 % 4)) || (e.out2 && (!al16p(e.out2) || e.ld_out2 % 4)))
     return TAGAN_E_UNSUPPORTED;

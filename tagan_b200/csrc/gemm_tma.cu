@@ -24,6 +24,7 @@
 // Out-of-range rows / columns / K tail are zero-filled by TMA itself, so there is no edge-tile code path.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -205,6 +206,34 @@ __device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int la
   const int64_t row0 = (int64_t)mt * BM + warp * 32 + (lane >> 3);
   const int cl = (lane & 7) * 4;
   const uint32_t tbase = ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+  if (e.mode == TAGAN_EPI_STORE_BF16) {
+    // acc + bias rounded to bf16 (RNE): the fused QKV projection of the bf16-storage mode; a lane's 4 columns are one 8-byte store
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(e.out0);
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      float4 v[8];
+      epi_load_chunk(tbase + (uint32_t)(cc * 32), stg, lane, v);
+      const int64_t c0 = n0 + cc * 32 + cl;
+      const bool cok = c0 < p.N;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cok && p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t grow = row0 + 4 * i;
+        if (!(cok && grow < p.M)) continue;
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x + b4.x, v[i].y + b4.y);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v[i].z + b4.z, v[i].w + b4.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(o16 + grow * e.ld_out0 + c0) = pk;
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar);
+    return;
+  }
   if (e.mode == TAGAN_EPI_RES_LN || e.mode == TAGAN_EPI_STORE) {
     const bool ln = e.mode == TAGAN_EPI_RES_LN && e.gamma != nullptr;
     float* tmp = e.out1 ? e.out1 : e.out0;

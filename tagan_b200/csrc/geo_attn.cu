@@ -13,6 +13,20 @@
 // HBM-bound: algorithmic bytes are nnz*(2*H*4+4) + N*(2*H*4+8h+8) forward.
 #include "common.cuh"
 
+// Storage type of the gathered operands Q, K, V.  This file is compiled twice: as is (fp32, the parity mode) and through
+// geo_attn_bf16.cu with TAGAN_GEO_BF16 defined (bf16 rows: half the gather bytes; scores, softmax and every accumulation stay
+// fp32, outputs and gradients are fp32).  The bf16 build exports the same entry points with a `_bf16` suffix.
+#ifdef TAGAN_GEO_BF16
+#include <cuda_bf16.h>
+typedef __nv_bfloat16 qkv_t;
+typedef uint16_t qkv_api_t;           // the C ABI carries bf16 rows as raw 16-bit words
+#define GEO_NAME(n) n##_bf16
+#else
+typedef float qkv_t;
+typedef float qkv_api_t;
+#define GEO_NAME(n) n
+#endif
+
 namespace {
 
 constexpr int WARPS_PER_BLOCK = 8;
@@ -126,6 +140,27 @@ __device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const float*
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) VecIO<VEC>::load(dst[c], base + c * 32 * VEC + lane * VEC);
 }
+#ifdef TAGAN_GEO_BF16
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
+// bf16 row: VEC contiguous bf16 per lane and chunk = one 2 / 4 / 8-byte load, widened to fp32 in registers
+template <int VEC, int NCHUNK>
+__device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const __nv_bfloat16* base, int lane) {
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    const __nv_bfloat16* p = base + c * 32 * VEC + lane * VEC;
+    if (VEC == 4) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+      dst[c][0] = bf16_bits_to_float(u.x & 0xffffu); dst[c][1 % VEC] = bf16_bits_to_float(u.x >> 16);
+      dst[c][2 % VEC] = bf16_bits_to_float(u.y & 0xffffu); dst[c][3 % VEC] = bf16_bits_to_float(u.y >> 16);
+    } else if (VEC == 2) {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+      dst[c][0] = bf16_bits_to_float(u & 0xffffu); dst[c][1 % VEC] = bf16_bits_to_float(u >> 16);
+    } else {
+      dst[c][0] = bf16_bits_to_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)));
+    }
+  }
+}
+#endif
 
 // Rows (or, in the column pass, source nodes) with more than HEAVY_THRESH entries are "heavy": the
 // warp-per-row kernels skip them and a second launch gives each of them a whole CTA -- its 8 warps take
@@ -175,7 +210,7 @@ struct RowCtx {
 };
 
 template <int METRIC, int VEC, int NCHUNK>
-__device__ __forceinline__ void init_row(RowCtx<METRIC, VEC, NCHUNK>& rc, const float* qrow, const float* metric_param,
+__device__ __forceinline__ void init_row(RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* qrow, const float* metric_param,
                                          int D, int lane) {
   rc.group = D / VEC;
   load_row<VEC, NCHUNK>(rc.q, qrow, lane);
@@ -196,8 +231,8 @@ __device__ __forceinline__ void init_row(RowCtx<METRIC, VEC, NCHUNK>& rc, const 
 
 // online-softmax walk over entries [beg,end) of one row
 template <int METRIC, int VEC, int NCHUNK>
-__device__ __forceinline__ void fwd_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float* __restrict__ K,
-                                         const float* __restrict__ V, int64_t ld, const int* __restrict__ col, int beg,
+__device__ __forceinline__ void fwd_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* __restrict__ K,
+                                         const qkv_t* __restrict__ V, int64_t ld, const int* __restrict__ col, int beg,
                                          int end, int lane, float (&m)[NCHUNK], float (&l)[NCHUNK],
                                          float (&acc)[NCHUNK][VEC]) {
   constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
@@ -234,7 +269,7 @@ __device__ __forceinline__ void fwd_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, 
 }
 
 template <int METRIC, int VEC, int NCHUNK>
-__device__ __forceinline__ void fwd_attn_pass(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float* __restrict__ K,
+__device__ __forceinline__ void fwd_attn_pass(const RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* __restrict__ K,
                                               int64_t ld, const int* __restrict__ col, int beg, int end, int lane,
                                               int heads, const float (&lse_c)[NCHUNK], float* __restrict__ attn) {
   for (int e = beg; e < end; ++e) {
@@ -252,7 +287,7 @@ __device__ __forceinline__ void fwd_attn_pass(const RowCtx<METRIC, VEC, NCHUNK>&
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas(VEC, NCHUNK))
-geo_attn_fwd_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+geo_attn_fwd_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
                     const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
                     const float* __restrict__ metric_param, float* __restrict__ ctx, float* __restrict__ lse,
                     float* __restrict__ attn) {
@@ -349,7 +384,7 @@ geo_attn_fwd_kernel(const float* __restrict__ Q, int64_t ldq, const float* __res
 template <int METRIC, int VEC, int NCHUNK>
 __device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float (&go)[NCHUNK][VEC],
                                              const float (&ls)[NCHUNK], const float (&dl)[NCHUNK],
-                                             const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+                                             const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
                                              const int* __restrict__ col, int beg, int end, int lane,
                                              float (&dq)[NCHUNK][VEC], float (&dpar)[NCHUNK]) {
   constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
@@ -387,7 +422,7 @@ __device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& 
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas(VEC, NCHUNK))
-geo_attn_bwd_row_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+geo_attn_bwd_row_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
                         const int* __restrict__ rowptr, const int* __restrict__ col, int N, int heads, int D,
                         const float* __restrict__ metric_param, const float* __restrict__ ctx,
                         const float* __restrict__ lse, const float* __restrict__ dctx, float* __restrict__ dQ,
@@ -482,7 +517,7 @@ geo_attn_bwd_row_kernel(const float* __restrict__ Q, int64_t ldq, const float* _
 template <int METRIC, int VEC, int NCHUNK>
 __device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], const float (&v)[NCHUNK][VEC],
                                              const float (&par)[NCHUNK], const int (&head)[NCHUNK], int group,
-                                             const float* __restrict__ Q, int64_t ldq, const float* __restrict__ dctx,
+                                             const qkv_t* __restrict__ Q, int64_t ldq, const float* __restrict__ dctx,
                                              const float* __restrict__ lse, const float* __restrict__ delta, int heads,
                                              const int* __restrict__ row_t, int beg, int end, int lane,
                                              float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC]) {
@@ -538,7 +573,7 @@ __device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], cons
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas(VEC, NCHUNK))
-geo_attn_bwd_col_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
+geo_attn_bwd_col_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
                         const int* __restrict__ rowptr_t, const int* __restrict__ row_t, int N, int heads, int D,
                         const float* __restrict__ metric_param, const float* __restrict__ lse,
                         const float* __restrict__ delta, const float* __restrict__ dctx, float* __restrict__ dK,
@@ -663,10 +698,13 @@ bool pick_shape(int H, int heads, Shape* s) {
 
 }  // namespace
 
-TAGAN_API int tagan_geo_attn_fwd_part(const float* Q, int64_t ldq, const float* K, const float* V, int64_t ldkv,
+TAGAN_API int GEO_NAME(tagan_geo_attn_fwd_part)(const qkv_api_t* Q_, int64_t ldq, const qkv_api_t* K_, const qkv_api_t* V_, int64_t ldkv,
                                       const int32_t* rowptr, const int32_t* col, int32_t n_rows, int32_t H,
                                       int32_t heads, int32_t metric, const float* metric_param, float* ctx, float* lse,
                                       float* attn, tagan_stream_t stream) {
+  const qkv_t* Q = reinterpret_cast<const qkv_t*>(Q_);
+  const qkv_t* K = reinterpret_cast<const qkv_t*>(K_);
+  const qkv_t* V = reinterpret_cast<const qkv_t*>(V_);
   if (!Q || !K || !V || !rowptr || !col || !ctx || !lse || n_rows < 0 || ldq < H || ldkv < H) return TAGAN_E_INVALID;
   Shape sh;
   if (!pick_shape(H, heads, &sh) || (ldq % sh.vec) || (ldkv % sh.vec)) return TAGAN_E_UNSUPPORTED;
@@ -680,19 +718,22 @@ TAGAN_API int tagan_geo_attn_fwd_part(const float* Q, int64_t ldq, const float* 
   return tagan_launch_status();
 }
 
-TAGAN_API int tagan_geo_attn_fwd(const float* Q, const float* K, const float* V, int64_t ld, const int32_t* rowptr,
+TAGAN_API int GEO_NAME(tagan_geo_attn_fwd)(const qkv_api_t* Q, const qkv_api_t* K, const qkv_api_t* V, int64_t ld, const int32_t* rowptr,
                                  const int32_t* col, int32_t N, int32_t H, int32_t heads, int32_t metric,
                                  const float* metric_param, float* ctx, float* lse, float* attn,
                                  tagan_stream_t stream) {
-  return tagan_geo_attn_fwd_part(Q, ld, K, V, ld, rowptr, col, N, H, heads, metric, metric_param, ctx, lse, attn, stream);
+  return GEO_NAME(tagan_geo_attn_fwd_part)(Q, ld, K, V, ld, rowptr, col, N, H, heads, metric, metric_param, ctx, lse, attn, stream);
 }
 
-TAGAN_API int tagan_geo_attn_bwd_part(const float* Q, int64_t ldq, const float* K, const float* V, int64_t ldkv,
+TAGAN_API int GEO_NAME(tagan_geo_attn_bwd_part)(const qkv_api_t* Q_, int64_t ldq, const qkv_api_t* K_, const qkv_api_t* V_, int64_t ldkv,
                                       const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
                                       const int32_t* row_t, int32_t n_rows, int32_t n_src, int32_t H, int32_t heads,
                                       int32_t metric, const float* metric_param, const float* ctx, const float* lse,
                                       const float* dctx, float* dQ, int64_t lddq, float* dK, float* dV, int64_t lddkv,
                                       float* delta_ws, float* dparam_ws, float* dparam, tagan_stream_t stream) {
+  const qkv_t* Q = reinterpret_cast<const qkv_t*>(Q_);
+  const qkv_t* K = reinterpret_cast<const qkv_t*>(K_);
+  const qkv_t* V = reinterpret_cast<const qkv_t*>(V_);
   if (!Q || !K || !V || !rowptr || !col || !rowptr_t || !row_t || !ctx || !lse || !dctx || !dQ || !dK || !dV ||
       !delta_ws || n_rows < 0 || n_src < 0 || ldq < H || ldkv < H || lddq < H || lddkv < H)
     return TAGAN_E_INVALID;
@@ -722,12 +763,12 @@ TAGAN_API int tagan_geo_attn_bwd_part(const float* Q, int64_t ldq, const float* 
   return tagan_launch_status();
 }
 
-TAGAN_API int tagan_geo_attn_bwd(const float* Q, const float* K, const float* V, int64_t ld, const int32_t* rowptr,
+TAGAN_API int GEO_NAME(tagan_geo_attn_bwd)(const qkv_api_t* Q, const qkv_api_t* K, const qkv_api_t* V, int64_t ld, const int32_t* rowptr,
                                  const int32_t* col, const int32_t* rowptr_t, const int32_t* row_t, int32_t N,
                                  int32_t H, int32_t heads, int32_t metric, const float* metric_param,
                                  const float* ctx, const float* lse, const float* dctx, float* dQ, float* dK,
                                  float* dV, int64_t ldd, float* delta_ws, float* dparam_ws, float* dparam,
                                  tagan_stream_t stream) {
-  return tagan_geo_attn_bwd_part(Q, ld, K, V, ld, rowptr, col, rowptr_t, row_t, N, N, H, heads, metric, metric_param,
+  return GEO_NAME(tagan_geo_attn_bwd_part)(Q, ld, K, V, ld, rowptr, col, rowptr_t, row_t, N, N, H, heads, metric, metric_param,
                                  ctx, lse, dctx, dQ, ldd, dK, dV, ldd, delta_ws, dparam_ws, dparam, stream);
 }

@@ -64,7 +64,7 @@ def _epi(mode, split=0, in0=None, ld_in0=0, in1=None, ld_in1=0, out0=None, ld_ou
     return e
 
 
-_EPI_STREAMS = {0: 1, 1: 3, 2: 4, 3: 4, 4: 5}     # [M,N]-sized tensors an epilogue reads + writes (algorithmic bytes)
+_EPI_STREAMS = {0: 1, 1: 3, 2: 4, 3: 4, 4: 5, 5: 0.5}     # [M,N]-sized tensors an epilogue reads + writes (algorithmic bytes)
 
 
 def gemm_fused(op, m, n, k, a, lda, a2, lda2, k1, b, ldb, bias, epi, dev):
@@ -143,7 +143,7 @@ def _rows2(x):
 # ------------------------------------------------------------------------------------------
 class _GeoLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ln1w, ln1b, wq, bq, wk, bk, wv, bv, wo, bo, ln2w, ln2b, metric_param, csrs, heads, metric):
+    def forward(ctx, x, ln1w, ln1b, wq, bq, wk, bk, wv, bv, wo, bo, ln2w, ln2b, metric_param, csrs, heads, metric, bf16=False):
         lib = _lib.load()
         rows = _rows2(x)
         r, hdim = rows.shape
@@ -157,18 +157,32 @@ class _GeoLayerFn(torch.autograd.Function):
         xn, mean1, rstd1 = _ln_plain(lib, rows, ln1w, ln1b)                        # :538-542
         w_qkv = torch.cat([wq, wk, wv], 0)
         b_qkv = torch.cat([bq, bk, bv], 0)
-        qkv = _e(r, 3 * hdim, dev=dev)
-        gemm(0, r, 3 * hdim, hdim, xn, hdim, w_qkv, hdim, b_qkv, qkv, 3 * hdim)     # :546-548
+        es = 2 if bf16 else 4                                                     # bytes per stored q/k/v element
+        if bf16:
+            # bf16-STORAGE mode: the projection is computed as always (3xTF32, fp32 accumulate) and rounded to bf16 (RNE) by
+            # the GEMM epilogue; kernel (a) gathers half the bytes and works in fp32
+            qkv = torch.empty(r, 3 * hdim, dtype=torch.bfloat16, device=dev)
+            if _use_fused_gemm() and r > 0 and _al(xn, w_qkv, b_qkv):
+                gemm_fused(0, r, 3 * hdim, hdim, xn, hdim, None, 0, 0, w_qkv, hdim, b_qkv,
+                           _epi(_lib.EPI_STORE_BF16, out0=qkv, ld_out0=3 * hdim), dev)
+            else:
+                tmp = _e(r, 3 * hdim, dev=dev)
+                gemm(0, r, 3 * hdim, hdim, xn, hdim, w_qkv, hdim, b_qkv, tmp, 3 * hdim)
+                qkv.copy_(tmp)
+        else:
+            qkv = _e(r, 3 * hdim, dev=dev)
+            gemm(0, r, 3 * hdim, hdim, xn, hdim, w_qkv, hdim, b_qkv, qkv, 3 * hdim)     # :546-548
         ctxv = _e(r, hdim, dev=dev)
         lse = _e(r, heads, dev=dev)
         ld = 3 * hdim
+        fwd_fn = lib.tagan_geo_attn_fwd_bf16 if bf16 else lib.tagan_geo_attn_fwd
         base, cbase, lbase = qkv.data_ptr(), ctxv.data_ptr(), lse.data_ptr()
         for t, csr in enumerate(csrs):
-            off = base + offs[t] * ld * 4
-            q, k, v = (C.c_void_p(off + i * hdim * 4) for i in range(3))
+            off = base + offs[t] * ld * es
+            q, k, v = (C.c_void_p(off + i * hdim * es) for i in range(3))
             ops.wait_csr(csr)
             with _timed("geo_attn_fwd"):
-                rc = lib.tagan_geo_attn_fwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), csr.num_nodes, hdim, heads, metric,
+                rc = fwd_fn(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), csr.num_nodes, hdim, heads, metric,
                                             _ptr(metric_param), C.c_void_p(cbase + offs[t] * hdim * 4),
                                             C.c_void_p(lbase + offs[t] * heads * 4), None, _stream())
             _lib.check(rc, "tagan_geo_attn_fwd")
@@ -176,7 +190,7 @@ class _GeoLayerFn(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         out, xsum, mean2, rstd2 = linear_res_ln(ctxv, wo, bo, rows, ln2w, ln2b, need_sum=need)   # :586-596
         ctx.save_for_backward(rows, xn, mean1, rstd1, qkv, ctxv, lse, xsum, mean2, rstd2, ln1w, w_qkv, wo, ln2w, metric_param)
-        ctx.csrs, ctx.heads, ctx.metric, ctx.shape, ctx.offs = csrs, heads, metric, x.shape, offs
+        ctx.csrs, ctx.heads, ctx.metric, ctx.shape, ctx.offs, ctx.bf16 = csrs, heads, metric, x.shape, offs, bf16
         return out.view(x.shape)
 
     @staticmethod
@@ -203,13 +217,15 @@ class _GeoLayerFn(torch.autograd.Function):
         dp_ws = _e(n, heads, dev=dev) if want_dp else None
         dparam_t = _e(t_steps, heads, dev=dev) if want_dp else None
         ld = 3 * hdim
+        es = 2 if ctx.bf16 else 4
+        bwd_fn = lib.tagan_geo_attn_bwd_bf16 if ctx.bf16 else lib.tagan_geo_attn_bwd
         base, dbase = qkv.data_ptr(), dqkv.data_ptr()
         for t, csr in enumerate(csrs):
-            off, doff = base + offs[t] * ld * 4, dbase + offs[t] * ld * 4
-            q, k, v = (C.c_void_p(off + i * hdim * 4) for i in range(3))
+            off, doff = base + offs[t] * ld * es, dbase + offs[t] * ld * 4
+            q, k, v = (C.c_void_p(off + i * hdim * es) for i in range(3))
             dq, dk, dv = (C.c_void_p(doff + i * hdim * 4) for i in range(3))
             with _timed("geo_attn_bwd"):
-                rc = lib.tagan_geo_attn_bwd(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.rowptr_t), _ptr(csr.row_t),
+                rc = bwd_fn(q, k, v, ld, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.rowptr_t), _ptr(csr.row_t),
                                             csr.num_nodes, hdim, heads, metric, _ptr(metric_param),
                                             C.c_void_p(ctxv.data_ptr() + offs[t] * hdim * 4),
                                             C.c_void_p(lse.data_ptr() + offs[t] * heads * 4),
@@ -226,7 +242,7 @@ class _GeoLayerFn(torch.autograd.Function):
         dparam = dparam_t.sum(0) if want_dp else None
         h = hdim
         return (d_o.view(ctx.shape), dln1w, dln1b, dw_qkv[:h], db_qkv[:h], dw_qkv[h:2 * h], db_qkv[h:2 * h],
-                dw_qkv[2 * h:], db_qkv[2 * h:], dwo, dbo, dln2w, dln2b, dparam, None, None, None)
+                dw_qkv[2 * h:], db_qkv[2 * h:], dwo, dbo, dln2w, dln2b, dparam, None, None, None, None)
 
 
 def geo_layer(ga, x, csrs):
@@ -236,7 +252,7 @@ def geo_layer(ga, x, csrs):
                              ga.k_linear.weight, ga.k_linear.bias, ga.v_linear.weight, ga.v_linear.bias,
                              ga.output_proj.weight, ga.output_proj.bias, ga.layer_norm2.weight, ga.layer_norm2.bias,
                              getattr(ga, "distance_param", None), list(csrs), ga.num_heads,
-                             ops.METRIC_ID[ga.distance_metric])
+                             ops.METRIC_ID[ga.distance_metric], getattr(ga, "qkv_storage", "fp32") == "bf16")
 
 
 # ------------------------------------------------------------------------------------------

@@ -58,6 +58,9 @@ class GeometricAttention(nn.Module):
             self.layer_norm2 = nn.LayerNorm(hidden_dim)
         self.attn_dropout = nn.Dropout(dropout)
         self.output_dropout = nn.Dropout(dropout)
+        # "fp32" (parity mode) or "bf16": the projected q/k/v rows are STORED in bf16 (half the gather traffic of kernel (a));
+        # all arithmetic, outputs and gradients stay fp32.  Separate tolerance, see DESIGN.md section 2.
+        self.qkv_storage = "fp32"
         if learnable_distance and distance_metric in ("gaussian_kernel", "rbf_kernel"):
             self.distance_param = nn.Parameter(torch.ones(num_heads))
         self._init_parameters()
@@ -77,7 +80,11 @@ class GeometricAttention(nn.Module):
 
     def _fused_ok(self) -> bool:
         """Stage-level fused path (fused.geo_layer): LayerNorm on, dropout an identity (eval() or p = 0)."""
-        return ops.FUSION and self.use_layer_norm and not (self.training and self.dropout_prob > 0)
+        ok = ops.FUSION and self.use_layer_norm and not (self.training and self.dropout_prob > 0)
+        if self.qkv_storage == "bf16" and not ok:
+            raise NotImplementedError("qkv_storage='bf16' runs through the stage-fused geometric layer only "
+                                      "(LayerNorm on, dropout inactive)")
+        return ok
 
     def _check_shape(self):
         if not ops.geo_shape_supported(self.hidden_dim, self.num_heads):
@@ -89,6 +96,8 @@ class GeometricAttention(nn.Module):
         """x ``[N,H]`` -> ``[N,H]`` (+ per-entry weights ``[nnz,h]`` aligned with ``csr.row/col``)."""
         self._check_shape()
         self._warn_attn_dropout()
+        if self.qkv_storage == "bf16" and return_attention_weights:
+            raise NotImplementedError("attention weights are exported by the fp32 path only (qkv_storage='fp32')")
         if self._fused_ok() and not return_attention_weights:
             return fused.geo_layer(self, x, [csr])
         ln = self.use_layer_norm
