@@ -28,15 +28,19 @@ namespace {
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
+// `rbw` warps share one (node, head) slot when T > 32: they load its K/V tile together and each takes the query-row blocks
+// rb = r, r + rbw, ... (T = 128: 4 warps per head instead of one warp walking 4 row blocks -- the kernel is bound by
+// instruction issue at low occupancy, not by memory).  `warps` counts SLOT groups; the CTA has warps * rbw warps.
 template <int D>
-__global__ void __launch_bounds__(MAX_WARPS * 32)
+__global__ void __launch_bounds__(GEN_MAX_THREADS)
 tattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                  int64_t B, int T, int heads, int64_t rsb, int64_t rst, const float* __restrict__ bias_t,
                  int64_t bias_bstride, MaskSpec ms, float* __restrict__ ctx, float* __restrict__ lse,
-                 float* __restrict__ attn, int TP, int warps) {
+                 float* __restrict__ attn, int TP, int warps, int rbw) {
   extern __shared__ __align__(16) float smem[];
   const int H = heads * D;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wfull = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = wfull / rbw, rw = wfull - w * rbw;   // slot group, row-block worker inside it
   const int PPW = 32 / TP;                       // pairs per warp (1 when T >= 17)
   const int sub = lane / TP, li = lane - sub * TP;
   const int slot_floats = 2 * T * D + ((T + 3) & ~3);
@@ -51,19 +55,19 @@ tattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
     for (int hb = 0; hb < heads; hb += warps * PPW) {
       const int hd = hb + w * PPW + sub;
       const bool pv = hd < heads;
-      __syncwarp();
+      if (rbw > 1) __syncthreads(); else __syncwarp();
       if (pv) {
         const int64_t base = b * rsb * ld + (int64_t)hd * D;
-        load_tile<D>(Ks, K + base, rst * ld, T, li, TP);
-        load_tile<D>(Vs, V + base, rst * ld, T, li, TP);
-        if (ms.ts) for (int t = li; t < T; t += TP) ts_s[t] = ms.ts[b * T + t];
+        load_tile<D>(Ks, K + base, rst * ld, T, li + rw * TP, TP * rbw);
+        load_tile<D>(Vs, V + base, rst * ld, T, li + rw * TP, TP * rbw);
+        if (ms.ts) for (int t = li + rw * TP; t < T; t += TP * rbw) ts_s[t] = ms.ts[b * T + t];
       }
-      __syncwarp();
+      if (rbw > 1) __syncthreads(); else __syncwarp();
       const uint8_t* mbase = nullptr;
       if (ms.mask && pv)
         mbase = ms.mask + ((int64_t)(ms.mask_b > 1 ? b : 0) * ms.mask_h + (ms.mask_h > 1 ? hd : 0)) * T * T;
       const float* bt = (bias_t && pv) ? bias_t + b * bias_bstride + (int64_t)hd * T * T : nullptr;
-      for (int rb = 0; rb < RB; ++rb) {
+      for (int rb = rw; rb < RB; rb += rbw) {
         const int i = rb * 32 + li;
         const bool rv = pv && i < T;
         float q[D], acc[D];
@@ -134,16 +138,17 @@ tattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
 // backward
 // ---------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(MAX_WARPS * 32)
+__global__ void __launch_bounds__(GEN_MAX_THREADS)
 tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                  int64_t B, int T, int heads, int64_t rsb, int64_t rst, const float* __restrict__ bias,
                  const float* __restrict__ bias_t, int64_t bias_bstride, MaskSpec ms, const float* __restrict__ ctx, const float* __restrict__ lse,
                  const float* __restrict__ dctx, float* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dV,
                  int64_t ldd, float* __restrict__ dbias_out /* per-node [B,h,T,T] or per-CTA partial [grid,h,T,T] */,
-                 int dbias_per_node, int TP, int warps) {
+                 int dbias_per_node, int TP, int warps, int rbw) {
   extern __shared__ __align__(16) float smem[];
   const int H = heads * D;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wfull = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = wfull / rbw, rw = wfull - w * rbw;   // slot group, row-block worker inside it (see tattn_fwd_kernel)
   const int PPW = 32 / TP;
   const int sub = lane / TP, li = lane - sub * TP;
   const int tpad = (T + 3) & ~3;
@@ -171,18 +176,19 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
     for (int hb = 0; hb < heads; hb += warps * PPW) {
       const int hd = hb + w * PPW + sub;
       const bool pv = hd < heads;
-      __syncwarp();
+      const int lw = li + rw * TP, nlw = TP * rbw;           // this lane among the lanes that share the slot
+      if (rbw > 1) __syncthreads(); else __syncwarp();
       if (pv) {
         const int64_t base = b * rsb * ld + (int64_t)hd * D;
-        load_tile<D>(Qs, Q + base, rst * ld, T, li, TP);
-        load_tile<D>(Ks, K + base, rst * ld, T, li, TP);
-        load_tile<D>(Vs, V + base, rst * ld, T, li, TP);
-        load_tile<D>(Gs, dctx + b * rsb * (int64_t)H + (int64_t)hd * D, rst * H, T, li, TP);
-        if (ms.ts) for (int t = li; t < T; t += TP) ts_s[t] = ms.ts[b * T + t];
+        load_tile<D>(Qs, Q + base, rst * ld, T, lw, nlw);
+        load_tile<D>(Ks, K + base, rst * ld, T, lw, nlw);
+        load_tile<D>(Vs, V + base, rst * ld, T, lw, nlw);
+        load_tile<D>(Gs, dctx + b * rsb * (int64_t)H + (int64_t)hd * D, rst * H, T, lw, nlw);
+        if (ms.ts) for (int t = lw; t < T; t += nlw) ts_s[t] = ms.ts[b * T + t];
       }
-      __syncwarp();
+      if (rbw > 1) __syncthreads(); else __syncwarp();
       if (pv) {
-        for (int t = li; t < T; t += TP) {
+        for (int t = lw; t < T; t += nlw) {
           const float* cp = ctx + (b * rsb + t * rst) * (int64_t)H + (int64_t)hd * D;
           float dl = 0.f;
 #pragma unroll
@@ -195,7 +201,7 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
           lse_s[t] = lse[(b * heads + hd) * T + t];
         }
       }
-      __syncwarp();
+      if (rbw > 1) __syncthreads(); else __syncwarp();
       const uint8_t* mbase = nullptr;
       if (ms.mask && pv)
         mbase = ms.mask + ((int64_t)(ms.mask_b > 1 ? b : 0) * ms.mask_h + (ms.mask_h > 1 ? hd : 0)) * T * T;
@@ -205,7 +211,7 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
       if (dbias_out && pv)
         db = dbias_out + (dbias_per_node ? b * hTT : (int64_t)blockIdx.x * hTT) + (int64_t)hd * T * T;
       // ---- phase 1: lane owns query row i -> dQ_i, dBias[i,:]
-      for (int rb = 0; rb < RB; ++rb) {
+      for (int rb = rw; rb < RB; rb += rbw) {
         const int i = rb * 32 + li;
         const bool rv = pv && i < T;
         float q[D], g[D], dq[D];
@@ -230,8 +236,11 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
             }
           }
           if (db && rv) {
-            float* o = db + (int64_t)i * T + j;
-            *o = dbias_per_node ? ds : *o + ds;     // (cta, head, i, j) is owned by exactly this lane
+            // (cta, head, i, j) is owned by exactly this lane.  The CTA-private partial table (shared-bias mode) is kept
+            // TRANSPOSED ([j][i]): lanes are consecutive i, so the read-modify-write is one 128-byte line per warp instead of 32
+            // sectors a stride of T apart (T = 128: this was most of the kernel's time); the reduction transposes it back
+            if (dbias_per_node) db[(int64_t)i * T + j] = ds;
+            else { float* o = db + (int64_t)j * T + i; *o += ds; }
           }
         }
         if (rv) {
@@ -241,7 +250,7 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
         }
       }
       // ---- phase 2: lane owns key row j -> dK_j, dV_j
-      for (int rb = 0; rb < RB; ++rb) {
+      for (int rb = rw; rb < RB; rb += rbw) {
         const int j = rb * 32 + li;
         const bool rv = pv && j < T;
         float k[D], v[D], dk[D], dv[D];
@@ -286,6 +295,17 @@ __global__ void reduce_parts(const float* __restrict__ partial, int parts, int64
   for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * n + x];
   out[x] = s;
 }
+// same, for partial tables stored [head][j][i] (the generic backward kernel): out[head][i][j]
+__global__ void reduce_parts_transposed(const float* __restrict__ partial, int parts, int heads, int T, float* __restrict__ out) {
+  const int64_t n = (int64_t)heads * T * T;
+  int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;        // index into the [head][j][i] layout (coalesced reads)
+  if (x >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * n + x];
+  const int64_t h = x / ((int64_t)T * T);
+  const int r = (int)(x - h * T * T), j = r / T, i = r - j * T;
+  out[(h * T + i) * T + j] = s;
+}
 
 // allones[0] = 1 iff all band tests pass for every node and every explicit mask byte is non-zero
 __global__ void mask_allones_kernel(const float* __restrict__ ts, int64_t B, int T, float band,
@@ -309,7 +329,7 @@ __global__ void mask_allones_kernel(const float* __restrict__ ts, int64_t B, int
 }
 __global__ void set_flag(int* flag, int v) { *flag = v; }
 
-struct Cfg { int TP, PPW, warps; size_t smem; };
+struct Cfg { int TP, PPW, warps, rbw; size_t smem; };
 bool make_cfg(int T, int D, int heads, int slot_floats, Cfg* c) {
   int TP = 32;
   if (T <= 16) { TP = 1; while (TP < T) TP <<= 1; if (TP < 4) TP = 4; }
@@ -321,7 +341,16 @@ bool make_cfg(int T, int D, int heads, int slot_floats, Cfg* c) {
   if (fit < 1) return false;
   int warps = want < fit ? want : fit;
   if (warps > MAX_WARPS) warps = MAX_WARPS;
+  // long sequences (more than one block of 32 query rows): up to 4 warps share a (node, head) slot, GEN_MAX_THREADS per CTA
+  int rbw = 1;
+  if (T > 32) {
+    const int rb = (T + 31) / 32;
+    rbw = rb < 4 ? rb : 4;
+    while (warps * rbw * 32 > GEN_MAX_THREADS && warps > 1) --warps;
+    while (warps * rbw * 32 > GEN_MAX_THREADS && rbw > 1) --rbw;
+  }
   c->warps = warps;
+  c->rbw = rbw;
   c->smem = per_warp * warps;
   return true;
 }
@@ -388,7 +417,7 @@ static int tattn_fwd_impl(const float* Q, const float* K, const float* V, int64_
   if (fast && tagan_tattn_fwd_fast_launch(D, c.TP, grid, c.warps * 32, c.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
                                           ctx, lse, attn))
     return tagan_launch_status();
-  DISPATCH_D(tattn_fwd_kernel, <<<grid, c.warps * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias_t, bias_bstride, ms, ctx, lse, attn, c.TP, c.warps))
+  DISPATCH_D(tattn_fwd_kernel, <<<grid, c.warps * c.rbw * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias_t, bias_bstride, ms, ctx, lse, attn, c.TP, c.warps, c.rbw))
   return tagan_launch_status();
 }
 
@@ -459,14 +488,17 @@ static int tattn_bwd_impl(const float* Q, const float* K, const float* V, int64_
   Cfg cf;                                                // the fast kernel parks P and dS in smem: larger slots
   const bool fast = T <= 32 && !per_node && make_cfg(T, D, heads, tattn_bwd_fast_slot_floats(T, D, c.TP), &cf) &&
                     cf.warps * cf.PPW >= heads && cf.smem <= 100 * 1024;
+  bool transposed_parts = false;
   if (fast && tagan_tattn_bwd_fast_launch(D, cf.TP, grid, cf.warps * 32, cf.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
                                           ctx, lse, dctx, dQ, dK, dV, ldd, db_target)) {
   } else {
-    DISPATCH_D(tattn_bwd_kernel, <<<grid, c.warps * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, bias_t, bias_bstride, ms, ctx, lse, dctx, dQ, dK, dV, ldd, db_target, per_node ? 1 : 0, c.TP, c.warps))
+    transposed_parts = true;
+    DISPATCH_D(tattn_bwd_kernel, <<<grid, c.warps * c.rbw * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, bias_t, bias_bstride, ms, ctx, lse, dctx, dQ, dK, dV, ldd, db_target, per_node ? 1 : 0, c.TP, c.warps, c.rbw))
   }
   if (dbias && !per_node) {
     const int64_t n = (int64_t)heads * T * T;
-    reduce_parts<<<ceil_div_i64(n, 256), 256, 0, st>>>(db_target, grid, n, dbias);
+    if (transposed_parts) reduce_parts_transposed<<<ceil_div_i64(n, 256), 256, 0, st>>>(db_target, grid, heads, T, dbias);
+    else reduce_parts<<<ceil_div_i64(n, 256), 256, 0, st>>>(db_target, grid, n, dbias);
   }
   return tagan_launch_status();
 }

@@ -5,6 +5,7 @@
 namespace tagan_tattn {
 
 constexpr int MAX_WARPS = 8;
+constexpr int GEN_MAX_THREADS = 512;   // generic kernels: up to 4 warps per (node, head) slot for T > 32
 constexpr int SMEM_LIMIT = 200 * 1024;
 
 struct MaskSpec {

@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--snapshots", type=int, default=0)
+    ap.add_argument("--nodes", type=int, default=0, help="override the node count (edges scale with it)")
+    ap.add_argument("--only", default="", help="comma-separated stage names")
     ap.add_argument("--out", default="gpurun_out/stages.jsonl")
     args = ap.parse_args()
     import tagan_b200
@@ -24,13 +26,14 @@ def main():
     dev = torch.device("cuda:0")
     w = synth.WORKLOADS[args.workload]
     t_steps = args.snapshots or w.snapshots
-    n, hdim = w.num_nodes, w.hidden
+    n, hdim = args.nodes or w.num_nodes, w.hidden
+    n_edges = int(w.num_edges * n / w.num_nodes)
     torch.manual_seed(0)
     layer = tagan_b200.TAGANLayer(hdim, w.heads, "euclidean").to(dev)
     layer.geometric.validate_indices = False
     gen = torch.Generator().manual_seed(0)
     x3 = torch.randn(t_steps, n, hdim, device=dev)
-    eis = [synth.random_edges(n, w.num_edges, gen, w.graph).to(dev) for _ in range(t_steps)]
+    eis = [synth.random_edges(n, n_edges, gen, w.graph).to(dev) for _ in range(t_steps)]
     ts = torch.arange(t_steps, dtype=torch.float32, device=dev).expand(n, t_steps)
     csrs = [ops.build_csr(ei, n) for ei in eis]
     go = torch.randn(t_steps, n, hdim, device=dev)
@@ -47,8 +50,13 @@ def main():
     modes = {"unfused": (False, False, False), "stage_fused_plain_gemm": (True, False, False),
              "stage_fused_gemm_epilogues": (True, True, False), "stage_fused_gemm_epilogues_fastmath": (True, True, True)}
     out = open(args.out, "w")
+    only = [x for x in args.only.split(",") if x]
     for sname, fn in stages.items():
+        if only and sname not in only:
+            continue
         for mname, (fus, fg, fm) in modes.items():
+            if mname in ("stage_fused_plain_gemm", "stage_fused_gemm_epilogues_fastmath"):
+                continue
             ops.FUSION, fused.FUSED_GEMM, fused.EPI_FAST_MATH = fus, fg, fm
             times_f, times_b = [], []
             try:

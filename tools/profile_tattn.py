@@ -22,14 +22,20 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--time-major", type=int, default=1)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--nodes", type=int, default=0, help="override the node count (config 5 is benchmarked on a 25k-node sample)")
+    ap.add_argument("--mask", default="causal", choices=["causal", "band"],
+                    help="band: shared integer timestamps 0..T-1 with the reference's +-10 band (what the bench layer resolves to)")
     a = ap.parse_args()
     w = synth.WORKLOADS[a.workload]
-    b, t, h, heads = w.num_nodes, w.snapshots, w.hidden, w.heads
+    b, t, h, heads = a.nodes or w.num_nodes, w.snapshots, w.hidden, w.heads
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     qkv = (torch.randn(b * t, 3 * h, device=dev) * 0.5).requires_grad_(True)
     bias = (torch.randn(heads, t, t, device=dev) * 0.1).requires_grad_(True)
     tmask = ops.TemporalMask(flags=1)
+    if a.mask == "band":
+        ts = torch.arange(t, dtype=torch.float32, device=dev).repeat(b, 1).contiguous()
+        tmask = ops.TemporalMask(flags=2 | 4, ts=ts, allones_flag=ops.mask_allones_flag(ts, None, b, t, 10.0, dev))
     dctx = torch.randn(b * t, h, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tf, tb = [], []
