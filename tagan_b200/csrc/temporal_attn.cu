@@ -31,8 +31,8 @@ namespace {
 // `rbw` warps share one (node, head) slot when T > 32: they load its K/V tile together and each takes the query-row blocks
 // rb = r, r + rbw, ... (T = 128: 4 warps per head instead of one warp walking 4 row blocks -- the kernel is bound by
 // instruction issue at low occupancy, not by memory).  `warps` counts SLOT groups; the CTA has warps * rbw warps.
-template <int D>
-__global__ void __launch_bounds__(GEN_MAX_THREADS)
+template <int D, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? GEN_MAX_THREADS : MAX_WARPS * 32)
 tattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                  int64_t B, int T, int heads, int64_t rsb, int64_t rst, const float* __restrict__ bias_t,
                  int64_t bias_bstride, MaskSpec ms, float* __restrict__ ctx, float* __restrict__ lse,
@@ -137,8 +137,8 @@ tattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
 // ---------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(GEN_MAX_THREADS)
+template <int D, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? GEN_MAX_THREADS : MAX_WARPS * 32)
 tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ld,
                  int64_t B, int T, int heads, int64_t rsb, int64_t rst, const float* __restrict__ bias,
                  const float* __restrict__ bias_t, int64_t bias_bstride, MaskSpec ms, const float* __restrict__ ctx, const float* __restrict__ lse,
@@ -343,7 +343,7 @@ bool make_cfg(int T, int D, int heads, int slot_floats, Cfg* c) {
   if (warps > MAX_WARPS) warps = MAX_WARPS;
   // long sequences (more than one block of 32 query rows): up to 4 warps share a (node, head) slot, GEN_MAX_THREADS per CTA
   int rbw = 1;
-  if (T > 32) {
+  if (T > 32 && D <= 32) {                 // (D = 64 keeps one warp per slot: its register footprint needs the 256-thread bound)
     const int rb = (T + 31) / 32;
     rbw = rb < 4 ? rb : 4;
     while (warps * rbw * 32 > GEN_MAX_THREADS && warps > 1) --warps;
@@ -361,13 +361,22 @@ bool check_shape(int T, int H, int heads, int* D) {
   return *D == 4 || *D == 8 || *D == 16 || *D == 32 || *D == 64;
 }
 
-#define DISPATCH_D(FN, ...)                    \
-  switch (D) {                                 \
-    case 4: FN<4> __VA_ARGS__; break;          \
-    case 8: FN<8> __VA_ARGS__; break;          \
-    case 16: FN<16> __VA_ARGS__; break;        \
-    case 32: FN<32> __VA_ARGS__; break;        \
-    default: FN<64> __VA_ARGS__; break;        \
+#define DISPATCH_D(FN, WIDE, ...)                                  \
+  if (WIDE) {                                                      \
+    switch (D) {                                                   \
+      case 4: FN<4, true> __VA_ARGS__; break;                      \
+      case 8: FN<8, true> __VA_ARGS__; break;                      \
+      case 16: FN<16, true> __VA_ARGS__; break;                    \
+      default: FN<32, true> __VA_ARGS__; break;                    \
+    }                                                              \
+  } else {                                                         \
+    switch (D) {                                                   \
+      case 4: FN<4, false> __VA_ARGS__; break;                     \
+      case 8: FN<8, false> __VA_ARGS__; break;                     \
+      case 16: FN<16, false> __VA_ARGS__; break;                   \
+      case 32: FN<32, false> __VA_ARGS__; break;                   \
+      default: FN<64, false> __VA_ARGS__; break;                   \
+    }                                                              \
   }
 
 template <typename KernelT>
@@ -401,12 +410,21 @@ static int tattn_fwd_impl(const float* Q, const float* K, const float* V, int64_
   const int grid = (int)(B < 148 * 8 ? B : 148 * 8);
   cudaStream_t st = as_stream(stream);
   int rc = 0;
-  switch (D) {
-    case 4: rc = set_smem(tattn_fwd_kernel<4>, c.smem); break;
-    case 8: rc = set_smem(tattn_fwd_kernel<8>, c.smem); break;
-    case 16: rc = set_smem(tattn_fwd_kernel<16>, c.smem); break;
-    case 32: rc = set_smem(tattn_fwd_kernel<32>, c.smem); break;
-    default: rc = set_smem(tattn_fwd_kernel<64>, c.smem); break;
+  if (c.rbw > 1) {
+    switch (D) {
+      case 4: rc = set_smem(tattn_fwd_kernel<4, true>, c.smem); break;
+      case 8: rc = set_smem(tattn_fwd_kernel<8, true>, c.smem); break;
+      case 16: rc = set_smem(tattn_fwd_kernel<16, true>, c.smem); break;
+      default: rc = set_smem(tattn_fwd_kernel<32, true>, c.smem); break;
+    }
+  } else {
+    switch (D) {
+      case 4: rc = set_smem(tattn_fwd_kernel<4, false>, c.smem); break;
+      case 8: rc = set_smem(tattn_fwd_kernel<8, false>, c.smem); break;
+      case 16: rc = set_smem(tattn_fwd_kernel<16, false>, c.smem); break;
+      case 32: rc = set_smem(tattn_fwd_kernel<32, false>, c.smem); break;
+      default: rc = set_smem(tattn_fwd_kernel<64, false>, c.smem); break;
+    }
   }
   if (rc) return rc;
   const bool shared_bias = bias_bstride == 0 && (bias == nullptr) == (bias_t == nullptr);
@@ -417,7 +435,7 @@ static int tattn_fwd_impl(const float* Q, const float* K, const float* V, int64_
   if (fast && tagan_tattn_fwd_fast_launch(D, c.TP, grid, c.warps * 32, c.smem, st, Q, K, V, ld, B, T, heads, rsb, rst, bias, ms,
                                           ctx, lse, attn))
     return tagan_launch_status();
-  DISPATCH_D(tattn_fwd_kernel, <<<grid, c.warps * c.rbw * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias_t, bias_bstride, ms, ctx, lse, attn, c.TP, c.warps, c.rbw))
+  DISPATCH_D(tattn_fwd_kernel, c.rbw > 1, <<<grid, c.warps * c.rbw * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias_t, bias_bstride, ms, ctx, lse, attn, c.TP, c.warps, c.rbw))
   return tagan_launch_status();
 }
 
@@ -477,12 +495,21 @@ static int tattn_bwd_impl(const float* Q, const float* K, const float* V, int64_
   MaskSpec ms{ts, mask_flags, band, allones_flag, mask, mask_b, mask_h};
   cudaStream_t st = as_stream(stream);
   int rc = 0;
-  switch (D) {
-    case 4: rc = set_smem(tattn_bwd_kernel<4>, c.smem); break;
-    case 8: rc = set_smem(tattn_bwd_kernel<8>, c.smem); break;
-    case 16: rc = set_smem(tattn_bwd_kernel<16>, c.smem); break;
-    case 32: rc = set_smem(tattn_bwd_kernel<32>, c.smem); break;
-    default: rc = set_smem(tattn_bwd_kernel<64>, c.smem); break;
+  if (c.rbw > 1) {
+    switch (D) {
+      case 4: rc = set_smem(tattn_bwd_kernel<4, true>, c.smem); break;
+      case 8: rc = set_smem(tattn_bwd_kernel<8, true>, c.smem); break;
+      case 16: rc = set_smem(tattn_bwd_kernel<16, true>, c.smem); break;
+      default: rc = set_smem(tattn_bwd_kernel<32, true>, c.smem); break;
+    }
+  } else {
+    switch (D) {
+      case 4: rc = set_smem(tattn_bwd_kernel<4, false>, c.smem); break;
+      case 8: rc = set_smem(tattn_bwd_kernel<8, false>, c.smem); break;
+      case 16: rc = set_smem(tattn_bwd_kernel<16, false>, c.smem); break;
+      case 32: rc = set_smem(tattn_bwd_kernel<32, false>, c.smem); break;
+      default: rc = set_smem(tattn_bwd_kernel<64, false>, c.smem); break;
+    }
   }
   if (rc) return rc;
   Cfg cf;                                                // the fast kernel parks P and dS in smem: larger slots
@@ -493,7 +520,7 @@ static int tattn_bwd_impl(const float* Q, const float* K, const float* V, int64_
                                           ctx, lse, dctx, dQ, dK, dV, ldd, db_target)) {
   } else {
     transposed_parts = true;
-    DISPATCH_D(tattn_bwd_kernel, <<<grid, c.warps * c.rbw * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, bias_t, bias_bstride, ms, ctx, lse, dctx, dQ, dK, dV, ldd, db_target, per_node ? 1 : 0, c.TP, c.warps, c.rbw))
+    DISPATCH_D(tattn_bwd_kernel, c.rbw > 1, <<<grid, c.warps * c.rbw * 32, c.smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, bias_t, bias_bstride, ms, ctx, lse, dctx, dQ, dK, dV, ldd, db_target, per_node ? 1 : 0, c.TP, c.warps, c.rbw))
   }
   if (dbias && !per_node) {
     const int64_t n = (int64_t)heads * T * T;
