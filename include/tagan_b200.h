@@ -71,6 +71,17 @@ int tagan_csr_build(const int64_t* edge_index, int64_t num_edges, int32_t num_no
                     int32_t* status, void* workspace, size_t workspace_bytes,
                     tagan_stream_t stream);
 
+/* Batched form: T snapshots (T <= 128) as ONE block-diagonal graph in one launch set -- snapshot t's nodes are rows
+ * [off_t, off_t + node_counts[t]) with off_t = sum of the previous counts, its column ids are offset the same way, so the
+ * result equals the per-snapshot CSRs concatenated (bit-exact) and kernel (a) runs ONCE over the stacked [sum N_t, 3H]
+ * projection.  src / dst / edge_counts / node_counts are HOST arrays (T device pointers to the int64 source / destination
+ * ids of each snapshot; negative ids wrap within their snapshot); they are read during the call only.
+ * Outputs have capacity sum(E_t) + sum(N_t); workspace = tagan_csr_workspace_bytes(sum E_t, sum N_t). */
+int tagan_csr_build_batched(const int64_t* const* src, const int64_t* const* dst, const int64_t* edge_counts,
+                            const int32_t* node_counts, int32_t T, int32_t* rowptr, int32_t* col, int32_t* row,
+                            int32_t* rowptr_t, int32_t* row_t, int32_t* perm_t, int32_t* status, void* workspace,
+                            size_t workspace_bytes, tagan_stream_t stream);
+
 /* Node-partitioned variant (single large graph): this rank owns the query rows
  * [row_begin, row_begin+num_rows); edges whose row lies elsewhere are skipped.  rowptr[num_rows+1], row[]
  * hold LOCAL row ids, col[] GLOBAL node ids (self loop of local row i = row_begin+i); the transposed CSR is

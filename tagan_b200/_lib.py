@@ -43,6 +43,7 @@ SIGNATURES = {
     "tagan_abi_version": (_i32, []),
     "tagan_csr_workspace_bytes": (_sz, [_i64, _i32]),
     "tagan_csr_build": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "tagan_csr_build_batched": (_i32, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "tagan_csr_build_part": (_i32, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "tagan_geo_attn_fwd_part": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "tagan_geo_attn_bwd_part": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,

@@ -141,6 +141,49 @@ __global__ void scatter_edges(const int64_t* __restrict__ ei, int64_t E, int n, 
   }
 }
 
+// ---- batched (block-diagonal) form: T snapshots as ONE graph whose node ids are noff[t] + local id.  Only the two kernels
+// that read edge_index differ; everything after the bucket scatter is the single-graph pipeline on sum(N_t) rows.
+constexpr int MAX_BATCH = 128;
+struct Batch {
+  int T;
+  const int64_t* src[MAX_BATCH];
+  const int64_t* dst[MAX_BATCH];
+  int64_t eoff[MAX_BATCH + 1];     // edge e of the concatenation belongs to snapshot t with eoff[t] <= e < eoff[t+1]
+  int noff[MAX_BATCH + 1];         // first global row of snapshot t
+};
+__device__ __forceinline__ int batch_find(const Batch& b, int64_t e) {
+  int lo = 0, hi = b.T;            // invariant: eoff[lo] <= e < eoff[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (b.eoff[mid] <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__global__ void count_rows_batched(const __grid_constant__ Batch b, int64_t E, int* __restrict__ cnt, int* __restrict__ status) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int t = batch_find(b, e);
+  const int64_t le = e - b.eoff[t];
+  const int n = b.noff[t + 1] - b.noff[t];
+  int r, c;
+  if (norm_index(b.src[t][le], n, &r) && norm_index(b.dst[t][le], n, &c)) atomicAdd(&cnt[b.noff[t] + r], 1);
+  else *status = 1;
+}
+__global__ void scatter_edges_batched(const __grid_constant__ Batch b, int64_t E, const int* __restrict__ off,
+                                      int* __restrict__ cursor, int* __restrict__ bucket) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int t = batch_find(b, e);
+  const int64_t le = e - b.eoff[t];
+  const int n = b.noff[t + 1] - b.noff[t];
+  int r, c;
+  if (norm_index(b.src[t][le], n, &r) && norm_index(b.dst[t][le], n, &c)) {
+    r += b.noff[t];
+    const int p = atomicAdd(&cursor[r], 1);
+    bucket[off[r] + p] = b.noff[t] + c;
+  }
+}
+
 // ---- per-segment rank sort.  UNIQUE: keep the first of each run of equal keys and pack them
 // at the segment start (count -> ucount[seg]); otherwise a stable full sort with a payload.
 constexpr int SORT_SMEM_KEYS = 8192;
@@ -376,12 +419,12 @@ TAGAN_API size_t tagan_csr_workspace_bytes(int64_t num_edges, int32_t num_nodes)
   return ws_layout(num_edges, num_nodes).total;
 }
 
-TAGAN_API int tagan_csr_build_part(const int64_t* edge_index, int64_t E, int32_t N, int32_t row_begin, int32_t R,
-                                   int32_t* rowptr, int32_t* col, int32_t* row, int32_t* rowptr_t, int32_t* row_t,
-                                   int32_t* perm_t, int32_t* status, void* workspace, size_t workspace_bytes,
-                                   tagan_stream_t stream) {
+static int csr_build_impl(const int64_t* edge_index, const Batch* batch, int64_t E, int32_t N, int32_t row_begin, int32_t R,
+                          int32_t* rowptr, int32_t* col, int32_t* row, int32_t* rowptr_t, int32_t* row_t,
+                          int32_t* perm_t, int32_t* status, void* workspace, size_t workspace_bytes,
+                          tagan_stream_t stream) {
   if (E < 0 || N < 0 || R < 0 || row_begin < 0 || row_begin + (int64_t)R > N || !rowptr || !col || !row || !status ||
-      (E > 0 && !edge_index))
+      (E > 0 && !edge_index && !batch))
     return TAGAN_E_INVALID;
   if (E + (int64_t)N >= 0x7fffffffLL) return TAGAN_E_UNSUPPORTED;
   const bool transpose = rowptr_t || row_t || perm_t;
@@ -412,10 +455,16 @@ TAGAN_API int tagan_csr_build_part(const int64_t* edge_index, int64_t E, int32_t
 
   fill_i32<<<gR, TB, 0, st>>>(cnt, 1, R);         // one self loop per local row
   fill_i32<<<gR, TB, 0, st>>>(cursor, 1, R);
-  if (E > 0) count_rows<<<gE, TB, 0, st>>>(edge_index, E, N, row_begin, R, cnt, status);
+  if (E > 0) {
+    if (batch) count_rows_batched<<<gE, TB, 0, st>>>(*batch, E, cnt, status);
+    else count_rows<<<gE, TB, 0, st>>>(edge_index, E, N, row_begin, R, cnt, status);
+  }
   exclusive_scan(cnt, off, R, scanws, st);
   place_self_loops<<<gR, TB, 0, st>>>(off, bucket, R, row_begin);
-  if (E > 0) scatter_edges<<<gE, TB, 0, st>>>(edge_index, E, N, row_begin, R, off, cursor, bucket);
+  if (E > 0) {
+    if (batch) scatter_edges_batched<<<gE, TB, 0, st>>>(*batch, E, off, cursor, bucket);
+    else scatter_edges<<<gE, TB, 0, st>>>(edge_index, E, N, row_begin, R, off, cursor, bucket);
+  }
   seg_sort_warp<true, false><<<gW, TB, 0, st>>>(off, bucket, nullptr, staged, nullptr, ucount, R);
   seg_sort_block<true, false><<<gHeavy, TB, 0, st>>>(off, bucket, nullptr, staged, flags, ucount, R);
   exclusive_scan(ucount, rowptr, R, scanws, st);
@@ -434,6 +483,38 @@ TAGAN_API int tagan_csr_build_part(const int64_t* edge_index, int64_t E, int32_t
     seg_sort_block<false, true><<<gHeavy, TB, 0, st>>>(rowptr_t, bucket, staged, row_t, perm_t, nullptr, N);
   }
   return tagan_launch_status();
+}
+
+TAGAN_API int tagan_csr_build_part(const int64_t* edge_index, int64_t E, int32_t N, int32_t row_begin, int32_t R,
+                                   int32_t* rowptr, int32_t* col, int32_t* row, int32_t* rowptr_t, int32_t* row_t,
+                                   int32_t* perm_t, int32_t* status, void* workspace, size_t workspace_bytes,
+                                   tagan_stream_t stream) {
+  return csr_build_impl(edge_index, nullptr, E, N, row_begin, R, rowptr, col, row, rowptr_t, row_t, perm_t, status, workspace,
+                        workspace_bytes, stream);
+}
+
+TAGAN_API int tagan_csr_build_batched(const int64_t* const* src, const int64_t* const* dst, const int64_t* edge_counts,
+                                      const int32_t* node_counts, int32_t T, int32_t* rowptr, int32_t* col, int32_t* row,
+                                      int32_t* rowptr_t, int32_t* row_t, int32_t* perm_t, int32_t* status, void* workspace,
+                                      size_t workspace_bytes, tagan_stream_t stream) {
+  if (T <= 0 || T > MAX_BATCH || !edge_counts || !node_counts || !src || !dst) return T > MAX_BATCH ? TAGAN_E_UNSUPPORTED : TAGAN_E_INVALID;
+  Batch b;
+  b.T = T;
+  b.eoff[0] = 0;
+  b.noff[0] = 0;
+  for (int t = 0; t < T; ++t) {
+    if (edge_counts[t] < 0 || node_counts[t] < 0 || (edge_counts[t] > 0 && (!src[t] || !dst[t]))) return TAGAN_E_INVALID;
+    b.src[t] = src[t];
+    b.dst[t] = dst[t];
+    b.eoff[t + 1] = b.eoff[t] + edge_counts[t];
+    const int64_t nn = (int64_t)b.noff[t] + node_counts[t];
+    if (nn >= 0x7fffffffLL) return TAGAN_E_UNSUPPORTED;
+    b.noff[t + 1] = (int)nn;
+  }
+  for (int t = T; t < MAX_BATCH; ++t) { b.src[t] = nullptr; b.dst[t] = nullptr; b.eoff[t + 1] = b.eoff[T]; b.noff[t + 1] = b.noff[T]; }
+  const int32_t N = b.noff[T];
+  return csr_build_impl(nullptr, &b, b.eoff[T], N, 0, N, rowptr, col, row, rowptr_t, row_t, perm_t, status, workspace,
+                        workspace_bytes, stream);
 }
 
 TAGAN_API int tagan_csr_build(const int64_t* edge_index, int64_t E, int32_t N, int32_t* rowptr, int32_t* col,

@@ -199,6 +199,12 @@ class TAGANGraphAttention(nn.Module):
             csrs = [ei if isinstance(ei, ops.CSR) else
                     ops.build_csr(ei.to(x3.device), n, transpose=torch.is_grad_enabled(), validate=True)
                     for ei in edge_indices]
+        elif (ops.BATCHED_CSR and self.geometric_attention._fused_ok() and len(edge_indices) <= ops.MAX_CSR_BATCH
+              and not any(isinstance(ei, ops.CSR) for ei in edge_indices)
+              and sum(int(ei.shape[-1]) for ei in edge_indices) + n * len(edge_indices) < 2 ** 31):
+            # the T snapshots as ONE block-diagonal graph: one CSR launch set and one kernel-(a) launch per pass
+            csrs = [ops.build_csr_batched_async(edge_indices, [n] * len(edge_indices), x3.device,
+                                                transpose=torch.is_grad_enabled())]
         else:                                             # sync-free: build on the side stream, under LN1 + QKV
             csrs = ops.build_csr_async(edge_indices, n, x3.device, transpose=torch.is_grad_enabled())
         return self.geometric_attention.forward_seq(x3, csrs)

@@ -200,8 +200,13 @@ class TAGANModel(nn.Module):
             pairs = [self._unpack(s) for s in graph_sequence]
             seq = PackedSequence.from_snapshots([p[0] for p in pairs], [p[1] for p in pairs]).to(dev)
         t_steps, sizes, maxn = seq.num_snapshots, seq.sizes, seq.max_nodes
-        csrs = [ops.build_csr(seq.edge_index(t), sizes[t], transpose=torch.is_grad_enabled(), validate=False)
-                for t in range(t_steps)]
+        batched = (ops.BATCHED_CSR and t_steps <= ops.MAX_CSR_BATCH
+                   and all(l.geometric_attention._fused_ok() for l in self.geometric_attention_layers))
+        if batched:                                       # ONE block-diagonal graph over the packed rows
+            csrs = [ops.build_csr_batched([seq.edge_index(t) for t in range(t_steps)], sizes, transpose=torch.is_grad_enabled())]
+        else:
+            csrs = [ops.build_csr(seq.edge_index(t), sizes[t], transpose=torch.is_grad_enabled(), validate=False)
+                    for t in range(t_steps)]
         x = ops.linear(seq.x, self.node_embedding.weight, self.node_embedding.bias)                      # model.py:233
         skip = x
         for i, layer in enumerate(self.geometric_attention_layers):                                         # :244-262

@@ -157,6 +157,74 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int, transpose: bool = True, 
     return CSR(num_nodes, e, rowptr, col, row, rowptr_t, row_t, perm_t, status)
 
 
+MAX_CSR_BATCH = 128
+BATCHED_CSR = True          # forward_seq / TAGANModel: one block-diagonal CSR + one kernel-(a) launch per pass for all snapshots
+
+
+def build_csr_batched(edge_indices, sizes, transpose: bool = True) -> CSR:
+    """ONE block-diagonal CSR for T <= 128 snapshots (``edge_indices[t]``: contiguous int64 ``[2,E_t]`` on the device,
+    ``sizes[t]`` nodes): rows / columns of snapshot t are offset by ``sum(sizes[:t])``, so it equals the per-snapshot CSRs
+    concatenated and kernel (a) runs once over the stacked rows.  One launch set instead of T (21 launches each)."""
+    lib = _lib.load()
+    t_steps = len(edge_indices)
+    if not 0 < t_steps <= MAX_CSR_BATCH:
+        raise ValueError("build_csr_batched: 1..%d snapshots" % MAX_CSR_BATCH)
+    eis = []
+    for ei in edge_indices:
+        if not ei.is_cuda:
+            raise RuntimeError("tagan_b200 has no CPU path: edge_index must live on a CUDA device")
+        if ei.dtype != torch.int64:
+            ei = ei.long()
+        if ei.numel() and (ei.dim() != 2 or ei.shape[0] != 2):
+            raise ValueError("edge_index must be [2,E]")
+        eis.append(ei if (ei.numel() == 0 or ei.stride(1) == 1) else ei.contiguous())   # column slices of one [2,E] are fine
+    dev = eis[0].device
+    ecounts = [int(ei.shape[1]) if ei.numel() else 0 for ei in eis]
+    e_tot, n_tot = sum(ecounts), int(sum(sizes))
+    if e_tot + n_tot >= 2 ** 31:
+        raise NotImplementedError("build_csr_batched: sum(E_t) + sum(N_t) must stay below 2^31")
+    src = (C.c_void_p * t_steps)(*[ei[0].data_ptr() if ec else None for ei, ec in zip(eis, ecounts)])
+    dst = (C.c_void_p * t_steps)(*[ei[1].data_ptr() if ec else None for ei, ec in zip(eis, ecounts)])
+    ec_arr = (C.c_int64 * t_steps)(*ecounts)
+    nc_arr = (C.c_int32 * t_steps)(*[int(s) for s in sizes])
+    cap = e_tot + n_tot
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(n_tot + 1, **i32)
+    col = torch.empty(max(cap, 1), **i32)
+    row = torch.empty(max(cap, 1), **i32)
+    status = torch.empty(1, **i32)
+    rowptr_t = row_t = perm_t = None
+    if transpose:
+        rowptr_t = torch.empty(n_tot + 1, **i32)
+        row_t = torch.empty(max(cap, 1), **i32)
+        perm_t = torch.empty(max(cap, 1), **i32)
+    ws = workspace(lib.tagan_csr_workspace_bytes(e_tot, n_tot), dev)
+    with _timed("csr_build"):
+        rc = lib.tagan_csr_build_batched(src, dst, ec_arr, nc_arr, t_steps, _ptr(rowptr), _ptr(col), _ptr(row), _ptr(rowptr_t),
+                                         _ptr(row_t), _ptr(perm_t), _ptr(status), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "tagan_csr_build_batched")
+    CALLS["n"] += 22 if transpose else 12
+    csr = CSR(n_tot, e_tot, rowptr, col, row, rowptr_t, row_t, perm_t, status)
+    csr._keepalive = eis                      # the kernels read the edge lists asynchronously
+    return csr
+
+
+def build_csr_batched_async(edge_indices, sizes, device, transpose: bool = True) -> CSR:
+    """``build_csr_batched`` on the side stream (it depends only on the edge lists, so it runs under LN1 + the QKV projection);
+    the returned CSR carries a ``ready`` event."""
+    main = torch.cuda.current_stream()
+    side = side_stream(device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        csr = build_csr_batched([ei.to(device) for ei in edge_indices], sizes, transpose=transpose)
+        for t in (csr.rowptr, csr.col, csr.row, csr.rowptr_t, csr.row_t, csr.perm_t, csr.status):
+            if t is not None:
+                t.record_stream(main)
+        csr.ready = torch.cuda.Event()
+        csr.ready.record(side)
+    return csr
+
+
 _SIDE = {}
 
 
