@@ -254,6 +254,17 @@ struct tagan_epilogue {
   float* rstd;
 };
 size_t tagan_gemm_fused_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k);
+/* Tuning knob for A/B measurements (default 1): NT / NN projections with K <= 128 keep the CTA's pre-split weight panel
+ * (B_hi, B_lo: K x 128 x 8 bytes) resident in shared memory for the whole persistent kernel, so only the activation
+ * tiles stream through L2; 0 restores the per-tile reload. */
+void tagan_gemm_set_weights_resident(int32_t on);
+/* Tuning knob (default 0 = off; measured slower at every distance): the TMA producer issues cp.async.bulk.prefetch.tensor (L2) for the streamed operand tiles this
+ * many 32-wide k-blocks ahead of the shared-memory ring; 0 switches the prefetch off. */
+void tagan_gemm_set_prefetch(int32_t kblocks);
+/* Debug aid (tools/trace_gemm.py): a device buffer of 16 x 512 int64 that CTA 0 of every following tcgen05 GEMM launch
+ * fills with clock64() stamps of its pipeline (per k-block: TMA issue, bytes landed, split done, MMA start, MMA issued; per
+ * tile: accumulator free, accumulator full, epilogue done).  NULL (default) switches it off. */
+void tagan_gemm_set_trace(void* buf);
 int tagan_gemm_fused(int32_t op /*0=NT,1=NN*/, int64_t m, int64_t n, int64_t k,
                      const float* A, int64_t lda, const float* A2, int64_t lda2, int64_t k1,
                      const float* B, int64_t ldb, const float* bias, const struct tagan_epilogue* epi,

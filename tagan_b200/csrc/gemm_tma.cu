@@ -129,6 +129,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
                : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
+}
+
+constexpr int TRACE_N = 512;
+#define TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < TRACE_N) p.trace[(slot) * TRACE_N + (idx)] = clock64(); } while (0)
+
 struct Params {
   int64_t M, N, K;
   const float* bias;
@@ -146,6 +154,11 @@ struct Params {
   int cta_acc;              // split-K: every CTA accumulates its splits into ITS OWN partial tile (read-modify-write, fp32
                             // round-to-nearest) instead of one partial tile per split
   int fused;                // the epilogue is epi (a tagan_epilogue mode), not the plain store through C
+  long long* trace;         // debug: CTA 0 writes clock64() stamps of its first TRACE_N k-blocks / tiles ([8][TRACE_N]) or null
+  int prefetch;             // the TMA producer asks L2 for the streamed operand tiles this many k-blocks ahead of the smem ring
+                            // (the ring holds 4 x 16 KB per operand per SM: too few bytes in flight to cover HBM latency)
+  int b_resident;           // the pre-split B panel of this CTA (K <= STAGES*BK) stays in the B slots of the stages for the
+                            // whole kernel: k-block kb in stage slot kb, loaded once; only A streams
   int64_t K1;               // > 0: A is the column concatenation [A (k < K1) | A2 (k >= K1)] (tmA / tmA2), NT only
   tagan_epilogue epi;       // fused epilogue (mode 0 = plain store / bias / accumulate through C)
 };
@@ -432,12 +445,14 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+  uint64_t* bres_bar = tmem_empty + ACC_STAGES + 1;
   const uint32_t epi_u32 = smem_u32(smem + (size_t)STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_bar[s], 1); mbar_init(&full_bar[s], SPLIT_WARPS); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
@@ -462,6 +477,60 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.b_resident && (int64_t)blockIdx.x < num_work) {
+        // the grid is a multiple of tiles_n, so this CTA's N panel never changes: its B_hi / B_lo k-blocks go into the B slots
+        // of stage 0..nkb-1 once (weights: L2 hits) and stay
+        const int n0 = (int)(blockIdx.x % p.tiles_n) * BN;
+        const int nkb = (int)((p.K + BK - 1) / BK);
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)(nkb * 2 * TILE_BYTES));
+        for (int kb = 0; kb < nkb; ++kb) {
+          uint8_t* st = smem + (size_t)kb * STAGE_BYTES;
+          if (!p.b_mn_major) {
+            tma_load_2d(st + TILE_BYTES, &tmB, kb * BK, n0, bres_bar);
+            tma_load_2d(st + 2 * TILE_BYTES, &tmB2, kb * BK, n0, bres_bar);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              tma_load_2d(st + TILE_BYTES + b * 4096, &tmB, n0 + 32 * b, kb * BK, bres_bar);
+              tma_load_2d(st + 2 * TILE_BYTES + b * 4096, &tmB2, n0 + 32 * b, kb * BK, bres_bar);
+            }
+          }
+        }
+      }
+      int tr_kb = 0;
+      // L2 prefetch iterator: the same (work item, k-block) sequence, p.prefetch k-blocks ahead
+      const bool pf_b = !p.b_presplit;                       // pre-split weights are L2 hits anyway
+      int64_t pw = blockIdx.x, pk0 = 0, pkend = 0;
+      auto pf_open = [&]() {
+        if (pw >= num_work) return;
+        const int ks = (int)(pw / ((int64_t)p.tiles_n * p.tiles_m));
+        pk0 = (int64_t)ks * p.k_per_split;
+        pkend = pk0 + p.k_per_split < p.K ? pk0 + p.k_per_split : p.K;
+      };
+      auto pf_step = [&]() {
+        while (pw < num_work && pk0 >= pkend) { pw += gridDim.x; pf_open(); }
+        if (pw >= num_work) return;
+        const int m0 = (int)((pw / p.tiles_n) % p.tiles_m) * BM, n0 = (int)(pw % p.tiles_n) * BN;
+        if (!p.a_mn_major) {
+          if (p.K1 > 0 && pk0 >= p.K1) tma_prefetch_2d(&tmA2, (int)(pk0 - p.K1), m0);
+          else tma_prefetch_2d(&tmA, (int)pk0, m0);
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) tma_prefetch_2d(&tmA, m0 + 32 * b, (int)pk0);
+        }
+        if (pf_b) {
+          if (!p.b_mn_major) tma_prefetch_2d(&tmB, (int)pk0, n0);
+          else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) tma_prefetch_2d(&tmB, n0 + 32 * b, (int)pk0);
+          }
+        }
+        pk0 += BK;
+      };
+      if (p.prefetch > 0) {
+        pf_open();
+        for (int i = 0; i < p.prefetch; ++i) pf_step();
+      }
       for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int nt = (int)(w % p.tiles_n);
         const int mt = (int)((w / p.tiles_n) % p.tiles_m);
@@ -470,9 +539,11 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         const int64_t kbeg = (int64_t)ks * p.k_per_split;
         const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
         for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+          if (p.prefetch > 0) pf_step();
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          TRACE(0, tr_kb); ++tr_kb;
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&raw_bar[stage], (p.b_presplit ? 3 : 2) * TILE_BYTES);
+          mbar_arrive_expect_tx(&raw_bar[stage], (p.b_resident ? 1 : p.b_presplit ? 3 : 2) * TILE_BYTES);
           if (!p.a_mn_major) {
             if (p.K1 > 0 && k0 >= p.K1) tma_load_2d(st, &tmA2, (int)(k0 - p.K1), m0, &raw_bar[stage]);
             else tma_load_2d(st, &tmA, (int)k0, m0, &raw_bar[stage]);
@@ -480,7 +551,9 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
 #pragma unroll
             for (int b = 0; b < 4; ++b) tma_load_2d(st + b * 4096, &tmA, m0 + 32 * b, (int)k0, &raw_bar[stage]);
           }
-          if (!p.b_mn_major) {
+          if (p.b_resident) {
+            // B is in place
+          } else if (!p.b_mn_major) {
             tma_load_2d(st + TILE_BYTES, &tmB, (int)k0, n0, &raw_bar[stage]);
             if (p.b_presplit) tma_load_2d(st + 2 * TILE_BYTES, &tmB2, (int)k0, n0, &raw_bar[stage]);
           } else {
@@ -498,7 +571,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
   } else if (warp >= SPLIT_WARP0) {
     // ============================== hi/lo split (smem -> smem) ==============================
     const int tt = threadIdx.x - SPLIT_WARP0 * 32;           // 0..255
-    int stage = 0;
+    int stage = 0, tr_kb = 0;
     uint32_t phase = 0;
     for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
@@ -507,6 +580,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       float csum = 0.f;                                      // this thread's row of A summed over its k-columns
       for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
         mbar_wait(&raw_bar[stage], phase);                   // TMA bytes have landed
+        if (tt == 0) TRACE(1, tr_kb);
         const uint32_t st_u32 = smem_u32(smem + (size_t)stage * STAGE_BYTES);
         {
           // ---- A: raw smem tile -> registers -> hi/lo -> tensor memory.  A warp owns TMEM lanes 32*(warp%4)..+31, so
@@ -559,6 +633,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
+        if (tt == 0) TRACE(2, tr_kb);
+        ++tr_kb;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (p.colsum_part != nullptr) {                        // bias gradient for free: A has just been read anyway
@@ -581,6 +657,9 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t idesc = p.idesc;
     const int passes = p.passes;
+    const bool bres = p.b_resident != 0;
+    int tr_kb = 0, tr_tile = 0;
+    if (bres && (int64_t)blockIdx.x < num_work) mbar_wait(bres_bar, 0);
     for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
       const int64_t kbeg = (int64_t)ks * p.k_per_split;
@@ -588,11 +667,14 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       const int nkb = kend > kbeg ? (int)((kend - kbeg + BK - 1) / BK) : 0;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator stage
       tc_fence_after();
+      if (lane == 0) TRACE(5, tr_tile);
+      ++tr_tile;
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sbase = smem0 + (uint32_t)stage * STAGE_BYTES;
+        if (lane == 0) TRACE(3, tr_kb);
+        const uint32_t sbase = smem0 + (uint32_t)(bres ? kb : stage) * STAGE_BYTES;     // B slot: resident k-block or the stage
         const uint32_t ta0 = tmem_base + (uint32_t)(A_TMEM_COL0 + stage * A_TMEM_STAGE_COLS);
         if (elect_one()) {
 #pragma unroll
@@ -617,6 +699,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           umma_commit(&empty_bar[stage]);                    // frees the stage when the MMAs retire
         }
         __syncwarp();
+        if (lane == 0) TRACE(4, tr_kb);
+        ++tr_kb;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (elect_one()) umma_commit(&tmem_full[acc]);         // accumulator complete -> epilogue
@@ -625,7 +709,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
     }
   } else {
     // ============================== epilogue ==============================
-    int acc = 0;
+    int acc = 0, tr_tile = 0;
     uint32_t acc_phase = 0;
     for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int nt = (int)(w % p.tiles_n);
@@ -636,6 +720,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       const int64_t n0 = (int64_t)nt * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (threadIdx.x == 0) TRACE(6, tr_tile);
       if (p.fused) {                                       // warp-uniform
         if (p.fused == 2) epilogue_fused<true>(p, warp, lane, acc, mt, n0, epi_u32, &tmem_empty[acc]);
         else epilogue_fused<false>(p, warp, lane, acc, mt, n0, epi_u32, &tmem_empty[acc]);
@@ -651,6 +736,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t r[32];
+        if (threadIdx.x == 0 && cc == 1) TRACE(8, tr_tile);
         if (has_k) {
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + cc * 32);
           asm volatile(
@@ -668,6 +754,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
+        if (threadIdx.x == 0 && cc == 1) TRACE(9, tr_tile);
         // registers (lane = row, 32 consecutive columns) -> padded smem tile -> row-contiguous 128-byte stores
         const uint32_t stg = epi_u32 + (uint32_t)(warp * (32 * EPI_PITCH) * 4);
         __syncwarp();
@@ -685,6 +772,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           float4 v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = lds128(src0 + (uint32_t)(i * 4 * EPI_PITCH * 4));
+          if (threadIdx.x == 0 && cc == 1) TRACE(10, tr_tile);
           float* orow = out + ((int64_t)mt * BM + warp * 32 + (lane >> 3)) * ldo + c0;
           if (rmw) {
             float4 o[8];
@@ -698,6 +786,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
             v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
             *reinterpret_cast<float4*>(orow + (int64_t)(i * 4) * ldo) = v[i];
           }
+          if (threadIdx.x == 0 && cc == 1) TRACE(11, tr_tile);
         } else {
           const bool direct = p.partial == nullptr;
           const bool acc_here = direct ? (p.accumulate != 0) : (p.cta_acc != 0);
@@ -734,6 +823,9 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (threadIdx.x == 0) TRACE(7, tr_tile);
+      if (lane == 0) TRACE(12 + warp, tr_tile);
+      ++tr_tile;
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -846,15 +938,21 @@ Plan make_plan(int64_t M, int64_t N, int64_t K) {
 
 
 // weights: hi = rn_tf32(w), lo = rn_tf32(w - hi), same [rows, ld] layout, done once per call (tiny)
+// hi / lo images of a weight matrix w[rows, cols]; TRANSPOSE writes them as [cols, rows] (an NN product's B = W[K,N] becomes
+// the K-major [N,K] operand of the NT path: the MN-major shared-memory layout costs the MMA half its rate)
+template <bool TRANSPOSE>
 __global__ void presplit_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ hi,
                                 float* __restrict__ lo, int64_t ldo) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
-  const int64_t r = i / cols, c = i - r * cols;
+  int64_t r, c;
+  if (TRANSPOSE) { c = i / rows; r = i - c * rows; }       // consecutive threads write consecutive elements of the output
+  else { r = i / cols; c = i - r * cols; }
   const float x = w[r * ld + c];
   const float h = tf32_rn(x);
-  hi[r * ldo + c] = h;
-  lo[r * ldo + c] = tf32_rn(x - h);
+  const int64_t o = TRANSPOSE ? c * ldo + r : r * ldo + c;
+  hi[o] = h;
+  lo[o] = tf32_rn(x - h);
 }
 
 constexpr int64_t PRESPLIT_MAX_ELEMS = 1 << 22;   // B operands up to 16 MB (weights) are pre-split
@@ -902,6 +1000,12 @@ bool tagan_gemm_tma_supported(int64_t M, int64_t N, int64_t K, const float* A, i
   return get_encode() != nullptr;
 }
 
+static int g_b_resident = 1, g_prefetch = 0;
+static long long* g_trace = nullptr;
+void tagan_gemm_tma_set_trace(void* buf) { g_trace = static_cast<long long*>(buf); }
+void tagan_gemm_tma_set_resident(int on) { g_b_resident = on; }
+void tagan_gemm_tma_set_prefetch(int kblocks) { g_prefetch = kblocks < 0 ? 0 : kblocks; }
+
 static inline int64_t presplit_ld(int64_t cols) { return (cols + 3) / 4 * 4; }
 static inline bool want_presplit(int32_t op, int64_t N, int64_t K) { return op != 2 && N * K <= PRESPLIT_MAX_ELEMS; }
 
@@ -914,8 +1018,7 @@ size_t tagan_gemm_tma_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t 
   Plan pl = make_plan(M, N, K);
   size_t b = pl.splits > 1 ? (size_t)pl.parts * (size_t)M * (size_t)N * sizeof(float) : 0;
   if (want_presplit(op, N, K)) {
-    const int64_t rows = op == 0 ? N : K, cols = op == 0 ? K : N;
-    b = (b + 255) / 256 * 256 + 2 * (size_t)rows * presplit_ld(cols) * sizeof(float) + 256;
+    b = (b + 255) / 256 * 256 + 2 * (size_t)N * presplit_ld(K) * sizeof(float) + 256;
   }
   return b;
 }
@@ -974,8 +1077,6 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   }
   if (p.partial) p.c_vec = (N % 4 == 0);
   else p.c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
-  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | ((uint32_t)p.b_mn_major << 16) |
-            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   CUtensorMap tmA, tmB, tmB2, tmA2;
   // NT: A[M,K], B[N,K] (K-major).  NN: A[M,K], B[K,N] (MN-major).  TN: A[K,M], B[K,N] (both MN-major).
   bool okA = p.a_mn_major ? make_map(&tmA, A, K, M, lda, true, true)
@@ -985,22 +1086,37 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   p.b_presplit = 0;
   bool okB;
   if (want_presplit(op, N, K) && passes != 1) {
-    const int64_t rows = op == 0 ? N : K, cols = op == 0 ? K : N, ldo = presplit_ld(cols);
+    // images are always [N, K] (K-major): an NN product's W[K,N] is transposed on the way
+    const int64_t rows = op == 0 ? N : K, cols = op == 0 ? K : N, ldo = presplit_ld(K);
     size_t off = pl.splits > 1 ? ((size_t)pl.parts * M * N * sizeof(float) + 255) / 256 * 256 : 0;
-    if (!workspace || workspace_bytes < off + 2 * (size_t)rows * ldo * sizeof(float)) return TAGAN_E_WORKSPACE;
+    if (!workspace || workspace_bytes < off + 2 * (size_t)N * ldo * sizeof(float)) return TAGAN_E_WORKSPACE;
     float* hi = reinterpret_cast<float*>(static_cast<char*>(workspace) + off);
-    float* lo = hi + rows * ldo;
-    okB = make_map(&tmB, hi, rows, cols, ldo, p.b_mn_major) && make_map(&tmB2, lo, rows, cols, ldo, p.b_mn_major);
+    float* lo = hi + N * ldo;
+    p.b_mn_major = 0;
+    okB = make_map(&tmB, hi, N, K, ldo, false) && make_map(&tmB2, lo, N, K, ldo, false);
     p.b_presplit = 1;
     // the tensor maps only need addresses: encode them first so that nothing is enqueued when encoding fails
-    if (okA && okB) presplit_kernel<<<ceil_div_i64(rows * cols, 256), 256, 0, st>>>(B, rows, cols, ldb, hi, lo, ldo);
+    if (okA && okB) {
+      if (op == 0) presplit_kernel<false><<<ceil_div_i64(rows * cols, 256), 256, 0, st>>>(B, rows, cols, ldb, hi, lo, ldo);
+      else presplit_kernel<true><<<ceil_div_i64(rows * cols, 256), 256, 0, st>>>(B, rows, cols, ldb, hi, lo, ldo);
+    }
   } else {
     okB = p.b_mn_major ? make_map(&tmB, B, K, N, ldb, true) : make_map(&tmB, B, N, K, ldb, false);
     tmB2 = tmB;
   }
   if (!okA || !okB) return TAGAN_E_UNSUPPORTED;
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | ((uint32_t)p.b_mn_major << 16) |
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   int64_t work = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits;
   int grid = (int)(work < 148 ? work : 148);
+  // resident weights: every work item of a CTA has the same N panel when the grid is a multiple of tiles_n
+  p.prefetch = g_prefetch;
+  p.trace = g_trace;
+  p.b_resident = 0;
+  if (g_b_resident && p.b_presplit && pl.splits == 1 && K <= (int64_t)STAGES * BK && pl.tiles_n <= 74 && work >= 2 * 148) {
+    p.b_resident = 1;
+    grid = 148 / pl.tiles_n * pl.tiles_n;
+  }
   gemm_tma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
   if (p.partial)
     tma_splitk_reduce<<<ceil_div_i64(M * N, 32), 256, 0, st>>>(p.partial, pl.parts, M, N, bias, C, ldc, accumulate);
