@@ -254,13 +254,15 @@ struct tagan_epilogue {
   float* rstd;
 };
 size_t tagan_gemm_fused_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k);
-/* Tuning knob for A/B measurements (default 1): NT / NN projections with K <= 128 keep the CTA's pre-split weight panel
- * (B_hi, B_lo: K x 128 x 8 bytes) resident in shared memory for the whole persistent kernel, so only the activation
- * tiles stream through L2; 0 restores the per-tile reload. */
-void tagan_gemm_set_weights_resident(int32_t on);
-/* Tuning knob (default 0 = off; measured slower at every distance): the TMA producer issues cp.async.bulk.prefetch.tensor (L2) for the streamed operand tiles this
- * many 32-wide k-blocks ahead of the shared-memory ring; 0 switches the prefetch off. */
-void tagan_gemm_set_prefetch(int32_t kblocks);
+/* Tuning knobs of the tcgen05 GEMM, for A/B measurements inside one process (boxes of the pool differ by ~15 %):
+ *   key 0  resident weights (default 1): NT / NN projections with K <= 128 keep the CTA's pre-split weight panel (B_hi, B_lo:
+ *          K x 128 x 8 bytes) in shared memory for the whole persistent kernel; only the activation tiles stream
+ *   key 1  L2 prefetch distance of the TMA producer in 32-wide k-blocks (default 0 = off: measured slower at every distance)
+ *   key 2  epilogue issues the TMEM load of the next 32-column chunk before storing the current one (default 0)
+ *   key 3  resident mode: activation smem slots are released by the split warps instead of the MMA commit (default 0)
+ *   key 4  suspend-time hint (ns) of the mbarrier waits, 0 = plain polling (default 10 000 000, as CUTLASS)
+ * Keys 1-3 made no difference or a small loss in same-process A/B runs (profiles/r02_SUMMARY.md); they stay for re-measurement. */
+void tagan_gemm_set_tuning(int32_t key, int32_t value);
 /* Debug aid (tools/trace_gemm.py): a device buffer of 16 x 512 int64 that CTA 0 of every following tcgen05 GEMM launch
  * fills with clock64() stamps of its pipeline (per k-block: TMA issue, bytes landed, split done, MMA start, MMA issued; per
  * tile: accumulator free, accumulator full, epilogue done).  NULL (default) switches it off. */

@@ -68,8 +68,7 @@ SIGNATURES = {
     "tagan_gemm_tn_colsum_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "tagan_gemm_tn_colsum": (_i32, [_i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _sz, _p]),
     "tagan_gemm_fused_workspace_bytes": (_sz, [_i32, _i64, _i64, _i64]),
-    "tagan_gemm_set_weights_resident": (None, [_i32]),
-    "tagan_gemm_set_prefetch": (None, [_i32]),
+    "tagan_gemm_set_tuning": (None, [_i32, _i32]),
     "tagan_gemm_set_trace": (None, [_p]),
     "tagan_gemm_fused": (_i32, [_i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p, C.POINTER(Epilogue), _i32,
                                 _p, _sz, _p]),

@@ -21,17 +21,14 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
                    const float* A2 = nullptr, int64_t lda2 = 0, int64_t K1 = 0, const tagan_epilogue* epi = nullptr,
                    int32_t epi_fast = 0);
 
-void tagan_gemm_tma_set_resident(int on);
-void tagan_gemm_tma_set_prefetch(int kblocks);
+void tagan_gemm_tma_set_tuning(int key, int value);
+/* tuning knobs of the tcgen05 GEMM for A/B measurements inside one process (tools/profile_gemm_shapes.py) */
+TAGAN_API void tagan_gemm_set_tuning(int32_t key, int32_t value) { tagan_gemm_tma_set_tuning(key, value); }
 void tagan_gemm_tma_set_trace(void* buf);
 /* debug: device buffer of 16 x 512 int64 that CTA 0 of every following tcgen05 GEMM launch fills with clock64() stamps
  * (per k-block: TMA issue, bytes landed, split done, MMA start, MMA issued; per tile: accumulator free, accumulator full,
  * epilogue done); null switches tracing off */
 TAGAN_API void tagan_gemm_set_trace(void* buf) { tagan_gemm_tma_set_trace(buf); }
-/* tuning knob: L2 prefetch distance of the TMA producer in 32-wide k-blocks (0 = off) */
-TAGAN_API void tagan_gemm_set_prefetch(int32_t kblocks) { tagan_gemm_tma_set_prefetch(kblocks); }
-/* tuning knob (profiling / A-B tests): keep the pre-split weight panel resident in shared memory (default on) */
-TAGAN_API void tagan_gemm_set_weights_resident(int32_t on) { tagan_gemm_tma_set_resident(on); }
 
 TAGAN_API size_t tagan_gemm_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_t k) {
   if (op < 0 || op > 2 || m < 0 || n < 0 || k < 0) return 0;

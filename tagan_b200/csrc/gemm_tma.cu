@@ -43,7 +43,8 @@ constexpr int TMEM_COLS = 512;                          // 256 (accumulators) + 
 static_assert(A_TMEM_COL0 + STAGES * A_TMEM_STAGE_COLS <= TMEM_COLS, "TMEM budget");
 constexpr int EPI_PITCH = 36;
 constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH * 4;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + (size_t)EPI_WARPS * EPI_STAGE_BYTES;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * EPI_STAGE_BYTES + 256;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -58,6 +59,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   do {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n }"
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+// same with a suspend-time hint: the hardware parks the polling thread until the phase completes (or the hint expires), so a
+// waiting role does not take issue slots from the epilogue / split warps of its scheduler
+__device__ __forceinline__ void mbar_wait_t(uint32_t ticks, uint64_t* bar, uint32_t parity) {
+  if (ticks == 0) { mbar_wait(bar, parity); return; }
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n }"
+                 : "=r"(ok) : "r"(addr), "r"(parity), "r"(ticks) : "memory");
   } while (!ok);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -137,6 +149,20 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, i
 constexpr int TRACE_N = 512;
 #define TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < TRACE_N) p.trace[(slot) * TRACE_N + (idx)] = clock64(); } while (0)
 
+// one 32-column chunk of the accumulator: lane = row, r[j] = column j of the chunk (asynchronous: tcgen05.wait::ld before use)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 struct Params {
   int64_t M, N, K;
   const float* bias;
@@ -157,6 +183,9 @@ struct Params {
   long long* trace;         // debug: CTA 0 writes clock64() stamps of its first TRACE_N k-blocks / tiles ([8][TRACE_N]) or null
   int prefetch;             // the TMA producer asks L2 for the streamed operand tiles this many k-blocks ahead of the smem ring
                             // (the ring holds 4 x 16 KB per operand per SM: too few bytes in flight to cover HBM latency)
+  uint32_t ticks;           // suspend-time hint of every mbarrier wait (0 = plain try_wait polling)
+  int epi_pipe;             // epilogue: issue the TMEM load of chunk cc+1 before the read-back / stores of chunk cc
+  int early_release;        // resident mode: the A smem slot is released by the split warps, the A TMEM slot by the MMA commit
   int b_resident;           // the pre-split B panel of this CTA (K <= STAGES*BK) stays in the B slots of the stages for the
                             // whole kernel: k-block kb in stage slot kb, loaded once; only A streams
   int64_t K1;               // > 0: A is the column concatenation [A (k < K1) | A2 (k >= K1)] (tmA / tmA2), NT only
@@ -215,7 +244,7 @@ template <bool FAST>
 __device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int lane, int acc, int mt, int64_t n0,
                                                uint32_t epi_u32, uint64_t* tmem_empty_bar) {
   const tagan_epilogue& e = p.epi;
-  const uint32_t stg = epi_u32 + (uint32_t)(warp * (32 * EPI_PITCH) * 4);
+  const uint32_t stg = epi_u32 + (uint32_t)(warp * EPI_STAGE_BYTES);
   const int64_t row0 = (int64_t)mt * BM + warp * 32 + (lane >> 3);
   const int cl = (lane & 7) * 4;
   const uint32_t tbase = ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
@@ -439,20 +468,22 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmA2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* raw_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* raw_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * EPI_STAGE_BYTES);
   uint64_t* full_bar = raw_bar + STAGES;
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
   uint64_t* bres_bar = tmem_empty + ACC_STAGES + 1;
-  const uint32_t epi_u32 = smem_u32(smem + (size_t)STAGES * STAGE_BYTES + 256);
+  uint64_t* sfree_bar = bres_bar + 1;                       // [STAGES] early release of the A smem slots (resident mode)
+  const uint32_t epi_u32 = smem_u32(smem + (size_t)STAGES * STAGE_BYTES);      // 1024-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_bar[s], 1); mbar_init(&full_bar[s], SPLIT_WARPS); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     mbar_init(bres_bar, 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&sfree_bar[s], SPLIT_WARPS);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
@@ -540,7 +571,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
         for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
           if (p.prefetch > 0) pf_step();
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_t(p.ticks, p.early_release ? &sfree_bar[stage] : &empty_bar[stage], phase ^ 1);
           TRACE(0, tr_kb); ++tr_kb;
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_arrive_expect_tx(&raw_bar[stage], (p.b_resident ? 1 : p.b_presplit ? 3 : 2) * TILE_BYTES);
@@ -579,7 +610,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
       float csum = 0.f;                                      // this thread's row of A summed over its k-columns
       for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-        mbar_wait(&raw_bar[stage], phase);                   // TMA bytes have landed
+        mbar_wait_t(p.ticks, &raw_bar[stage], phase);                   // TMA bytes have landed
         if (tt == 0) TRACE(1, tr_kb);
         const uint32_t st_u32 = smem_u32(smem + (size_t)stage * STAGE_BYTES);
         {
@@ -610,6 +641,15 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
               lo[kk] = __float_as_uint(tf32_rn(x - h));
               csum += x;
             }
+          }
+          if (p.early_release) {
+            // the raw tile is in registers: hand the smem slot back to the TMA producer now (the arrive is a release: the
+            // shared-memory reads above are ordered before it), then wait for the MMAs that read this TMEM slot four
+            // k-blocks ago -- the smem ring now only holds bytes in flight, the TMEM ring the operands waiting for the MMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sfree_bar[stage]);
+            mbar_wait_t(p.ticks, &empty_bar[stage], phase ^ 1);
+            tc_fence_after();
           }
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                  (uint32_t)(A_TMEM_COL0 + stage * A_TMEM_STAGE_COLS + half * 16);
@@ -659,19 +699,19 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
     const int passes = p.passes;
     const bool bres = p.b_resident != 0;
     int tr_kb = 0, tr_tile = 0;
-    if (bres && (int64_t)blockIdx.x < num_work) mbar_wait(bres_bar, 0);
+    if (bres && (int64_t)blockIdx.x < num_work) mbar_wait_t(p.ticks, bres_bar, 0);
     for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int ks = (int)(w / ((int64_t)p.tiles_n * p.tiles_m));
       const int64_t kbeg = (int64_t)ks * p.k_per_split;
       const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
       const int nkb = kend > kbeg ? (int)((kend - kbeg + BK - 1) / BK) : 0;
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator stage
+      mbar_wait_t(p.ticks, &tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator stage
       tc_fence_after();
       if (lane == 0) TRACE(5, tr_tile);
       ++tr_tile;
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_t(p.ticks, &full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) TRACE(3, tr_kb);
         const uint32_t sbase = smem0 + (uint32_t)(bres ? kb : stage) * STAGE_BYTES;     // B slot: resident k-block or the stage
@@ -718,7 +758,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       const int64_t kbeg = (int64_t)ks * p.k_per_split;
       const bool has_k = kbeg < p.K;
       const int64_t n0 = (int64_t)nt * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_t(p.ticks, &tmem_full[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 0) TRACE(6, tr_tile);
       if (p.fused) {                                       // warp-uniform
@@ -733,22 +773,18 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       // C += A.B (the GRU scan's per-step GEMMs), or this CTA's partial tile += its next split
       const bool rmw = p.partial == nullptr ? (p.accumulate != 0) : (p.cta_acc != 0);
       const bool bias_vec = p.partial == nullptr && p.bias != nullptr;       // host guarantees 16-byte alignment when c_vec
+      // The TMEM load of chunk cc+1 is issued as soon as the registers of chunk cc have gone to shared memory, so its latency
+      // runs under the shared-memory read-back and the global stores of chunk cc (the epilogue warps are the slowest stage of
+      // the pipeline for the [T*N, 128] projections: tools/trace_gemm.py).
+      uint32_t r[32];
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+      const bool pipe = p.epi_pipe != 0;
+      if (has_k && pipe) tmem_ld32(taddr0, r);
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
-        uint32_t r[32];
         if (threadIdx.x == 0 && cc == 1) TRACE(8, tr_tile);
         if (has_k) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + cc * 32);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr)
-              : "memory");
+          if (!pipe) tmem_ld32(taddr0 + (uint32_t)(cc * 32), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #pragma unroll
@@ -756,12 +792,13 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         }
         if (threadIdx.x == 0 && cc == 1) TRACE(9, tr_tile);
         // registers (lane = row, 32 consecutive columns) -> padded smem tile -> row-contiguous 128-byte stores
-        const uint32_t stg = epi_u32 + (uint32_t)(warp * (32 * EPI_PITCH) * 4);
+        const uint32_t stg = epi_u32 + (uint32_t)(warp * EPI_STAGE_BYTES);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           sts128(stg + (uint32_t)((lane * EPI_PITCH + j) * 4),
                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        if (has_k && pipe && cc + 1 < BN / 32) tmem_ld32(taddr0 + (uint32_t)((cc + 1) * 32), r);
         __syncwarp();
         const int64_t c0 = n0 + cc * 32 + (lane & 7) * 4;
         const uint32_t src0 = stg + (uint32_t)(((lane >> 3) * EPI_PITCH + (lane & 7) * 4) * 4);
@@ -1000,11 +1037,16 @@ bool tagan_gemm_tma_supported(int64_t M, int64_t N, int64_t K, const float* A, i
   return get_encode() != nullptr;
 }
 
-static int g_b_resident = 1, g_prefetch = 0;
+static int g_b_resident = 1, g_prefetch = 0, g_epi_pipe = 0, g_early_release = 0, g_wait_ticks = 0x989680;
+void tagan_gemm_tma_set_tuning(int key, int value) {
+  if (key == 0) g_b_resident = value;
+  else if (key == 1) g_prefetch = value < 0 ? 0 : value;
+  else if (key == 2) g_epi_pipe = value;
+  else if (key == 3) g_early_release = value;
+  else if (key == 4) g_wait_ticks = value;
+}
 static long long* g_trace = nullptr;
 void tagan_gemm_tma_set_trace(void* buf) { g_trace = static_cast<long long*>(buf); }
-void tagan_gemm_tma_set_resident(int on) { g_b_resident = on; }
-void tagan_gemm_tma_set_prefetch(int kblocks) { g_prefetch = kblocks < 0 ? 0 : kblocks; }
 
 static inline int64_t presplit_ld(int64_t cols) { return (cols + 3) / 4 * 4; }
 static inline bool want_presplit(int32_t op, int64_t N, int64_t K) { return op != 2 && N * K <= PRESPLIT_MAX_ELEMS; }
@@ -1111,10 +1153,14 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   int grid = (int)(work < 148 ? work : 148);
   // resident weights: every work item of a CTA has the same N panel when the grid is a multiple of tiles_n
   p.prefetch = g_prefetch;
+  p.epi_pipe = g_epi_pipe;
+  p.ticks = (uint32_t)g_wait_ticks;
+  p.early_release = 0;
   p.trace = g_trace;
   p.b_resident = 0;
   if (g_b_resident && p.b_presplit && pl.splits == 1 && K <= (int64_t)STAGES * BK && pl.tiles_n <= 74 && work >= 2 * 148) {
     p.b_resident = 1;
+    p.early_release = g_early_release;
     grid = 148 / pl.tiles_n * pl.tiles_n;
   }
   gemm_tma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """The projection shapes of one config-3 step in isolation (CUDA events, L2 flushed between launches, median): time,
 algorithmic GB/s, and -- for the NT / NN shapes with K <= 128 -- the same launch with the resident weight panel switched
-off (``tagan_gemm_set_weights_resident(0)``).  Each result is also checked against a float64 matmul on a row sample."""
+off (``tagan_gemm_set_tuning``).  Each result is also checked against a float64 matmul on a row sample."""
 import argparse
 import json
 import os
@@ -16,8 +16,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=1_600_000)
     ap.add_argument("--hidden", type=int, default=128)
-    ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--prefetch", type=int, nargs="+", default=[8, 0, 4, 16, 32])
+    ap.add_argument("--reps", type=int, default=9)
     ap.add_argument("--out", default="gpurun_out/gemm_shapes.jsonl")
     args = ap.parse_args()
     from tagan_b200 import _lib, ops
@@ -55,12 +54,14 @@ def main():
         lda, ldb = a.shape[1], b.shape[1]
         rec = {"case": "%s_%dx%dx%d" % (name, m, n, k)}
         nbytes = 4 * (a.numel() + c.numel() + b.numel())
-        modes = [(1, pf) for pf in args.prefetch] + ([(0, args.prefetch[0])] if op != 2 and k <= 128 else [])
-        for mode, pf in modes:
-            lib.tagan_gemm_set_weights_resident(mode)
-            lib.tagan_gemm_set_prefetch(pf)
+        # (resident, epilogue pipelining, early release, wait ticks)
+        modes = [(1, 0, 0, 0x989680), (1, 0, 0, 0), (1, 0, 0, 1000), (1, 1, 1, 0x989680)]
+        for mode in modes:
+            for key, val in zip((0, 2, 3, 4), mode):
+                lib.tagan_gemm_set_tuning(key, val)
+            c.fill_(float("nan"))
             ms = timeit(lambda: ops.gemm(op, m, n, k, a, lda, b, ldb, bias, c, n))
-            key = ("resident" if (mode and op != 2 and k <= 128) else "streamed") + "_pf%d" % pf
+            key = "res%d_pipe%d_early%d_ticks%d" % mode 
             rec[key + "_ms"] = round(ms, 4)
             # float64 check on a sample of rows
             idx = torch.randint(0, m, (256,), device=dev)
@@ -75,8 +76,8 @@ def main():
             err = float((c[idx].double() - ref).abs().max() / ref.abs().max())
             rec[key + "_relerr"] = err
             assert err < 2e-5, (rec, err)
-        lib.tagan_gemm_set_weights_resident(1)
-        lib.tagan_gemm_set_prefetch(8)
+        for key, val in ((0, 1), (2, 0), (3, 0), (4, 0x989680)):
+            lib.tagan_gemm_set_tuning(key, val)
         print(json.dumps(rec), flush=True)
         out.write(json.dumps(rec) + "\n")
 
