@@ -54,8 +54,8 @@ def main():
         lda, ldb = a.shape[1], b.shape[1]
         rec = {"case": "%s_%dx%dx%d" % (name, m, n, k)}
         nbytes = 4 * (a.numel() + c.numel() + b.numel())
-        # (resident, epilogue pipelining, early release, wait ticks)
-        modes = [(1, 0, 0, 0x989680), (1, 0, 0, 0), (1, 0, 0, 1000), (1, 1, 1, 0x989680)]
+        # (resident weights, epilogue pipelining, early smem release, mbarrier suspend hint)
+        modes = [(1, 0, 0, 0x989680), (0, 0, 0, 0x989680), (1, 1, 0, 0x989680), (1, 0, 1, 0x989680), (1, 0, 0, 0)]
         for mode in modes:
             for key, val in zip((0, 2, 3, 4), mode):
                 lib.tagan_gemm_set_tuning(key, val)
