@@ -603,13 +603,18 @@ def run_ours(args):
     peak, peak_src = peaks()
     t_fwd = statistics.mean(kt["geo_attn_fwd"]) * 1e-3
     t_bwd = statistics.mean(kt["geo_attn_bwd"]) * 1e-3
-    ach_bwd = bytes_bwd / t_bwd / 1e9
-    ach_fwd = bytes_fwd / t_fwd / 1e9
+    # snapshots one launch covers: T with the block-diagonal CSR (one launch per pass), 1 with per-snapshot launches
+    snaps_fwd = t_steps * args.steps / max(1, len(kt["geo_attn_fwd"]))
+    snaps_bwd = t_steps * args.steps / max(1, len(kt["geo_attn_bwd"]))
+    launch_bytes_fwd, launch_bytes_bwd = bytes_fwd * snaps_fwd, bytes_bwd * snaps_bwd
+    ach_bwd = launch_bytes_bwd / t_bwd / 1e9
+    ach_fwd = launch_bytes_fwd / t_fwd / 1e9
     roofline = {"kernel": "geo_attn_bwd (row pass + column pass)", "bound": "hbm", "achieved": ach_bwd, "peak": peak,
                 "unit": "GB/s", "frac": ach_bwd / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_bwd, "avg_launch_ms": t_bwd * 1e3,
-                "geo_attn_fwd": {"achieved": ach_fwd, "frac": ach_fwd / peak, "algorithmic_bytes_per_launch": bytes_fwd,
-                                 "avg_launch_ms": t_fwd * 1e3},
+                "algorithmic_bytes_per_launch": launch_bytes_bwd, "avg_launch_ms": t_bwd * 1e3,
+                "snapshots_per_launch": snaps_bwd, "algorithmic_bytes_per_snapshot": bytes_bwd,
+                "geo_attn_fwd": {"achieved": ach_fwd, "frac": ach_fwd / peak, "algorithmic_bytes_per_launch": launch_bytes_fwd,
+                                 "avg_launch_ms": t_fwd * 1e3, "snapshots_per_launch": snaps_fwd},
                 "share_of_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
                 "timed_in": "eager pass of the same K steps (CUDA events around every library call) run immediately "
                             "before the timed region; shares are relative to the timed step; csr_build runs on a side "
