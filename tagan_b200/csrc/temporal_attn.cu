@@ -67,9 +67,18 @@ tattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
       if (ms.mask && pv)
         mbase = ms.mask + ((int64_t)(ms.mask_b > 1 ? b : 0) * ms.mask_h + (ms.mask_h > 1 ? hd : 0)) * T * T;
       const float* bt = (bias_t && pv) ? bias_t + b * bias_bstride + (int64_t)hd * T * T : nullptr;
+      const bool windowed = mbase == nullptr && TP == 32;           // one slot per warp, no explicit mask tensor
+      const bool sorted = windowed && (ms.flags & 2) && ms.ts && pv && ts_sorted_warp(ts_s, T, lane);
       for (int rb = rw; rb < RB; rb += rbw) {
         const int i = rb * 32 + li;
         const bool rv = pv && i < T;
+        int jlo = 0, jhi = T - 1;
+        if (windowed) {                                              // the warp's union of key windows
+          int lo = T, hi = -1;
+          if (rv) valid_window(ms, causal, ms.ts ? ts_s : nullptr, sorted, T, i, true, &lo, &hi);
+          jlo = __reduce_min_sync(FULL_MASK, lo);
+          jhi = __reduce_max_sync(FULL_MASK, hi);
+        }
         float q[D], acc[D];
         float m = -INFINITY, l = 0.f;
 #pragma unroll
@@ -85,7 +94,7 @@ tattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
 #pragma unroll
           for (int c = 0; c < D; ++c) q[c] = 0.f;
         }
-        for (int j = 0; j < T; ++j) {
+        for (int j = jlo; j <= jhi; ++j) {
           const bool kv = rv && key_valid(ms, causal, ms.ts ? ts_s : nullptr, mbase, T, i, j);
           if (!__any_sync(FULL_MASK, kv)) continue;
           float s = -INFINITY;
@@ -210,15 +219,26 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
       float* db = nullptr;
       if (dbias_out && pv)
         db = dbias_out + (dbias_per_node ? b * hTT : (int64_t)blockIdx.x * hTT) + (int64_t)hd * T * T;
+      // per-node bias gradients are written for every (i, j), so only the shared-bias mode may skip positions
+      const bool windowed2 = mbase == nullptr && TP == 32;         // phase 2 (dK, dV) may always skip
+      const bool windowed = windowed2 && !want_pn;
+      const bool sorted = windowed2 && (ms.flags & 2) && ms.ts && pv && ts_sorted_warp(ts_s, T, lane);
       // ---- phase 1: lane owns query row i -> dQ_i, dBias[i,:]
       for (int rb = rw; rb < RB; rb += rbw) {
         const int i = rb * 32 + li;
         const bool rv = pv && i < T;
+        int jlo = 0, jhi = T - 1;
+        if (windowed) {
+          int lo = T, hi = -1;
+          if (rv) valid_window(ms, causal, ms.ts ? ts_s : nullptr, sorted, T, i, true, &lo, &hi);
+          jlo = __reduce_min_sync(FULL_MASK, lo);
+          jhi = __reduce_max_sync(FULL_MASK, hi);
+        }
         float q[D], g[D], dq[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) { q[c] = rv ? Qs[i * D + c] : 0.f; g[c] = rv ? Gs[i * D + c] : 0.f; dq[c] = 0.f; }
         const float ls = rv ? lse_s[i] : 0.f, dl = rv ? del_s[i] : 0.f;
-        for (int j = 0; j < T; ++j) {
+        for (int j = jlo; j <= jhi; ++j) {
           const bool kv = rv && key_valid(ms, causal, ms.ts ? ts_s : nullptr, mbase, T, i, j);
           if (!__any_sync(FULL_MASK, kv) && !want_pn) continue;
           float ds = 0.f;
@@ -240,7 +260,7 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
             // TRANSPOSED ([j][i]): lanes are consecutive i, so the read-modify-write is one 128-byte line per warp instead of 32
             // sectors a stride of T apart (T = 128: this was most of the kernel's time); the reduction transposes it back
             if (dbias_per_node) db[(int64_t)i * T + j] = ds;
-            else { float* o = db + (int64_t)j * T + i; *o += ds; }
+            else if (kv) { float* o = db + (int64_t)j * T + i; *o += ds; }   // the partial table starts at zero: masked pairs add nothing
           }
         }
         if (rv) {
@@ -256,7 +276,14 @@ tattn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
         float k[D], v[D], dk[D], dv[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) { k[c] = rv ? Ks[j * D + c] : 0.f; v[c] = rv ? Vs[j * D + c] : 0.f; dk[c] = 0.f; dv[c] = 0.f; }
-        for (int i = 0; i < T; ++i) {
+        int ilo = 0, ihi = T - 1;
+        if (windowed2) {                                              // the warp's union of row windows (dBias is phase 1's)
+          int lo = T, hi = -1;
+          if (rv) valid_window(ms, causal, ms.ts ? ts_s : nullptr, sorted, T, j, false, &lo, &hi);
+          ilo = __reduce_min_sync(FULL_MASK, lo);
+          ihi = __reduce_max_sync(FULL_MASK, hi);
+        }
+        for (int i = ilo; i <= ihi; ++i) {
           const bool kv = rv && key_valid(ms, causal, ms.ts ? ts_s : nullptr, mbase, T, i, j);
           if (!__any_sync(FULL_MASK, kv)) continue;
           if (kv) {

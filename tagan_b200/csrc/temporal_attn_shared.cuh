@@ -26,6 +26,39 @@ __device__ __forceinline__ bool key_valid(const MaskSpec& ms, bool causal, const
   return v;
 }
 
+// Conservative index window [lo, hi] outside of which key_valid(., .) is false for row / key `x` (the generic kernels then
+// walk the warp's union of windows instead of all T positions; every position inside is still tested with key_valid, so a
+// loose bound only costs time).  Band masks bound the window only when the node's timestamps are non-decreasing
+// (`ts_sorted`: checked per node, NaNs fail the check); an explicit mask tensor gives no bound.
+// upper_side: x is a query row and the window is over keys (causal: j <= x); else x is a key and the window is over rows.
+__device__ __forceinline__ void valid_window(const MaskSpec& ms, bool causal, const float* ts_s, bool ts_sorted, int T, int x,
+                                             bool upper_side, int* lo_out, int* hi_out) {
+  int lo = 0, hi = T - 1;
+  if (causal) { if (upper_side) hi = x; else lo = x; }
+  if ((ms.flags & 2) && ts_s && ts_sorted && x < T) {
+    const float tx = ts_s[x];
+    // key_valid tests fl(|ts_i - ts_j|) <= band; the thresholds are widened by a few ulps of the larger operand (and the
+    // window by one position) so that rounding can never exclude a position that test accepts
+    const float slack = 4.f * 1.1920929e-7f * fmaxf(fabsf(tx), fabsf(ms.band));
+    const float tlo = tx - ms.band - slack, thi = tx + ms.band + slack;
+    int a = 0, b = T;                                      // first index with ts >= tlo
+    while (a < b) { const int m = (a + b) >> 1; if (ts_s[m] < tlo) a = m + 1; else b = m; }
+    lo = max(lo, a - 1);
+    a = 0; b = T;                                          // first index with ts > thi
+    while (a < b) { const int m = (a + b) >> 1; if (ts_s[m] <= thi) a = m + 1; else b = m; }
+    hi = min(hi, a);
+  }
+  *lo_out = max(lo, 0);
+  *hi_out = min(hi, T - 1);
+}
+// all lanes of the warp: are ts_s[0..T) non-decreasing (false if any NaN)?
+__device__ __forceinline__ bool ts_sorted_warp(const float* ts_s, int T, int lane) {
+  bool ok = true;
+  for (int t = lane + 1; t < T; t += 32) ok = ok && (ts_s[t] >= ts_s[t - 1]);
+  if (T > 0 && lane == 0) ok = ok && (ts_s[0] == ts_s[0]);
+  return __all_sync(0xffffffffu, ok);
+}
+
 // floats of shared memory per (head) slot of the fast backward kernel: Q,K,V,dO tiles, P and dS (pitch TP+1), ts
 __host__ __device__ inline int tattn_bwd_fast_slot_floats(int T, int D, int TP) {
   return 4 * T * D + 2 * TP * (TP + 1) + ((T + 3) & ~3) + (((2 * TP * (TP + 1)) & 3) ? 4 - ((2 * TP * (TP + 1)) & 3) : 0);

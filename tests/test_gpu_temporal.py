@@ -81,7 +81,7 @@ def test_temporal_attention_vs_reference_golden(dev, golden):
 
 @pytest.mark.parametrize("b,t,hidden,heads", [(33, 16, 128, 8), (7, 32, 128, 4), (5, 48, 64, 4), (3, 128, 128, 8),
                                               (9, 5, 64, 4), (4, 16, 256, 8), (6, 11, 40, 5), (6, 11, 64, 4), (5, 9, 256, 8)])
-@pytest.mark.parametrize("mode", ["shared_ts", "no_ts_causal", "per_node_ts", "mask3d"])
+@pytest.mark.parametrize("mode", ["shared_ts", "no_ts_causal", "per_node_ts", "mask3d", "unsorted_ts", "boundary_ts"])
 def test_temporal_attention_vs_oracle_shapes(dev, b, t, hidden, heads, mode):
     import tagan_b200
     torch.manual_seed(b * 1000 + t)
@@ -98,6 +98,10 @@ def test_temporal_attention_vs_oracle_shapes(dev, b, t, hidden, heads, mode):
         ts = torch.arange(t).float().repeat(b, 1)
     elif mode == "per_node_ts":
         ts = torch.cumsum(torch.rand(b, t) * 2.5, dim=1)
+    elif mode == "unsorted_ts":                      # band mask on non-monotone times: no key window can be derived
+        ts = (torch.rand(1, t) * 40.0).repeat(b, 1)
+    elif mode == "boundary_ts":                      # sorted, duplicates, gaps of exactly the band width (|dt| == 10 is valid)
+        ts = (torch.div(torch.arange(t), 3, rounding_mode="floor").float() * 10.0).repeat(b, 1)
     elif mode == "mask3d":
         mask = torch.maximum((torch.rand(b, t, t) > 0.5).float(), torch.eye(t).unsqueeze(0))
     sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in layer.state_dict().items()}
