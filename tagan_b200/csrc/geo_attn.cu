@@ -38,9 +38,33 @@ template <int METRIC> struct MetricTraits {
   static constexpr bool kParam = METRIC == TAGAN_METRIC_GAUSSIAN || METRIC == TAGAN_METRIC_RBF;
 };
 
+// The three kernels are instruction-issue-bound at config 3 (ncu: 69 % issue-active, ~100 instructions per gathered entry,
+// L2 36 %, DRAM 45 %: profiles/r02_ncu_geo_batched_raw.csv), so the per-entry arithmetic uses the one-instruction SFU forms:
+// exp(x) = ex2.approx(x * log2 e), sqrt.approx, approximate division.  Each is good to ~2 ulp (|s - max| <= 30 adds
+// ~2e-6 relative to a probability), two orders of magnitude inside the rtol 1e-4 parity bar.
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// group sum with the group size known at compile time (GROUP = 0: runtime loop); the walks below are instantiated for the
+// common sizes 4 and 8 (D = 16 / 32 with 4 floats per lane) and fall back to the runtime form otherwise
+template <int GROUP>
+__device__ __forceinline__ float group_sum_t(float v, int group) {
+  if (GROUP == 0) return group_sum(v, group);
+#pragma unroll
+  for (int o = GROUP >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
 // Per-(entry, head) score and the partial sums its backward needs.
 //   p1: q.k (dot/cos) | sum (q-k)^2 (sq family) | sum |q-k| (manhattan);  p2: k.k (cos only)
-template <int METRIC, int VEC>
+template <int METRIC, int VEC, int GROUP = 0>
 __device__ __forceinline__ float score_from_vectors(const float* q, const float* k, int group, float par, float qnorm,
                                                     float& p1, float& p2) {
   using MT = MetricTraits<METRIC>;
@@ -52,8 +76,8 @@ __device__ __forceinline__ float score_from_vectors(const float* q, const float*
     else if (MT::kManhattan) a += fabsf(q[i] - k[i]);
     else { float d = q[i] - k[i]; a = fmaf(d, d, a); }
   }
-  a = group_sum(a, group);
-  if (MT::kCos) b = group_sum(b, group);
+  a = group_sum_t<GROUP>(a, group);
+  if (MT::kCos) b = group_sum_t<GROUP>(b, group);
   p1 = a; p2 = b;
   if (METRIC == TAGAN_METRIC_SCALED_DOT) return a * par;            // par = 1/sqrt(D)
   if (METRIC == TAGAN_METRIC_DOT) return a;
@@ -64,7 +88,7 @@ __device__ __forceinline__ float score_from_vectors(const float* q, const float*
     u = fminf(fmaxf(u, -1.f), 1.f);
     return METRIC == TAGAN_METRIC_COSINE_SIM ? u : -(1.f - u);
   }
-  if (METRIC == TAGAN_METRIC_EUCLIDEAN) return -sqrtf(a + 1e-8f);
+  if (METRIC == TAGAN_METRIC_EUCLIDEAN) return -fast_sqrt(a + 1e-8f);
   if (METRIC == TAGAN_METRIC_SQ_EUCLIDEAN) return -a;
   if (METRIC == TAGAN_METRIC_MANHATTAN) return -a;
   if (METRIC == TAGAN_METRIC_GAUSSIAN) return expf(-a / (2.f * par * par));   // par = sigma
@@ -112,7 +136,7 @@ __device__ __forceinline__ float accum_score_grad(float g, const float* q, const
   }
   // squared-distance family: d(score)/dq = coef * (q - k), d/dk = -coef * (q - k)
   float coef, dpar = 0.f;
-  if (METRIC == TAGAN_METRIC_EUCLIDEAN) coef = g / s;                 // s = -sqrt(sq+eps)
+  if (METRIC == TAGAN_METRIC_EUCLIDEAN) coef = __fdividef(g, s);      // s = -sqrt(sq+eps)
   else if (METRIC == TAGAN_METRIC_SQ_EUCLIDEAN) coef = -2.f * g;
   else if (METRIC == TAGAN_METRIC_GAUSSIAN) {
     float is2 = 1.f / (par * par);
@@ -229,12 +253,13 @@ __device__ __forceinline__ void init_row(RowCtx<METRIC, VEC, NCHUNK>& rc, const 
   }
 }
 
-// online-softmax walk over entries [beg,end) of one row
-template <int METRIC, int VEC, int NCHUNK>
-__device__ __forceinline__ void fwd_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* __restrict__ K,
-                                         const qkv_t* __restrict__ V, int64_t ld, const int* __restrict__ col, int beg,
-                                         int end, int lane, float (&m)[NCHUNK], float (&l)[NCHUNK],
-                                         float (&acc)[NCHUNK][VEC]) {
+// online-softmax walk over entries [beg,end) of one row.  U gathered entries are in flight per warp; the running maximum is
+// updated once per group of U entries (one rescale of l / acc per group instead of one per entry).
+template <int METRIC, int VEC, int NCHUNK, int GROUP>
+__device__ __forceinline__ void fwd_walk_t(const RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* __restrict__ K,
+                                           const qkv_t* __restrict__ V, int64_t ld, const int* __restrict__ col, int beg,
+                                           int end, int lane, float (&m)[NCHUNK], float (&l)[NCHUNK],
+                                           float (&acc)[NCHUNK][VEC]) {
   constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
   for (int base = beg; base < end; base += 32) {
     const int n = min(32, end - base);
@@ -248,24 +273,40 @@ __device__ __forceinline__ void fwd_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, 
         load_row<VEC, NCHUNK>(vv[u], V + (int64_t)cj * ld, lane);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (j + u < n) {
+      for (int c = 0; c < NCHUNK; ++c) {
+        float sv[U];
+        float mn = m[c];
 #pragma unroll
-          for (int c = 0; c < NCHUNK; ++c) {
-            float p1, p2;
-            const float s = score_from_vectors<METRIC, VEC>(rc.q[c], kk[u][c], rc.group, rc.par[c], rc.qn[c], p1, p2);
-            const float mn = fmaxf(m[c], s);
-            const float sc = expf(m[c] - mn);
-            const float p = expf(s - mn);
-            l[c] = fmaf(l[c], sc, p);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[c][i] = fmaf(acc[c][i], sc, p * vv[u][c][i]);
-            m[c] = mn;
-          }
+        for (int u = 0; u < U; ++u) {
+          float p1, p2;
+          sv[u] = score_from_vectors<METRIC, VEC, GROUP>(rc.q[c], kk[u][c], rc.group, rc.par[c], rc.qn[c], p1, p2);
+          if (j + u >= n) sv[u] = -INFINITY;                 // padding slot of the last group (a duplicate of entry n-1)
+          mn = fmaxf(mn, sv[u]);
         }
+        const float sc = fast_exp(m[c] - mn);                 // m = -inf on the first group: exp(-inf) = 0
+        l[c] *= sc;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[c][i] *= sc;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float p = fast_exp(sv[u] - mn);
+          l[c] += p;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[c][i] = fmaf(p, vv[u][c][i], acc[c][i]);
+        }
+        m[c] = mn;
       }
     }
   }
+}
+template <int METRIC, int VEC, int NCHUNK>
+__device__ __forceinline__ void fwd_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* __restrict__ K,
+                                         const qkv_t* __restrict__ V, int64_t ld, const int* __restrict__ col, int beg,
+                                         int end, int lane, float (&m)[NCHUNK], float (&l)[NCHUNK],
+                                         float (&acc)[NCHUNK][VEC]) {
+  if (rc.group == 4) fwd_walk_t<METRIC, VEC, NCHUNK, 4>(rc, K, V, ld, col, beg, end, lane, m, l, acc);
+  else if (rc.group == 8) fwd_walk_t<METRIC, VEC, NCHUNK, 8>(rc, K, V, ld, col, beg, end, lane, m, l, acc);
+  else fwd_walk_t<METRIC, VEC, NCHUNK, 0>(rc, K, V, ld, col, beg, end, lane, m, l, acc);
 }
 
 template <int METRIC, int VEC, int NCHUNK>
@@ -381,8 +422,8 @@ geo_attn_fwd_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __res
 }
 
 // ---- row pass: dQ[i] = sum_e ds_e * dscore/dq, delta[i,h] = dctx_i . ctx_i, optional dparam partials.
-template <int METRIC, int VEC, int NCHUNK>
-__device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float (&go)[NCHUNK][VEC],
+template <int METRIC, int VEC, int NCHUNK, int GROUP>
+__device__ __forceinline__ void bwd_row_walk_t(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float (&go)[NCHUNK][VEC],
                                              const float (&ls)[NCHUNK], const float (&dl)[NCHUNK],
                                              const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
                                              const int* __restrict__ col, int beg, int end, int lane,
@@ -405,12 +446,12 @@ __device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& 
 #pragma unroll
           for (int c = 0; c < NCHUNK; ++c) {
             float p1, p2;
-            const float s = score_from_vectors<METRIC, VEC>(rc.q[c], kk[u][c], rc.group, rc.par[c], rc.qn[c], p1, p2);
-            const float a = expf(s - ls[c]);
+            const float s = score_from_vectors<METRIC, VEC, GROUP>(rc.q[c], kk[u][c], rc.group, rc.par[c], rc.qn[c], p1, p2);
+            const float a = fast_exp(s - ls[c]);
             float dp = 0.f;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) dp = fmaf(go[c][i], vv[u][c][i], dp);
-            dp = group_sum(dp, rc.group);
+            dp = group_sum_t<GROUP>(dp, rc.group);
             const float ds = a * (dp - dl[c]);
             dpar[c] += accum_score_grad<METRIC, VEC, true>(ds, rc.q[c], kk[u][c], s, p1, p2, rc.par[c], rc.qn[c], dq[c]);
           }
@@ -418,6 +459,17 @@ __device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& 
       }
     }
   }
+}
+
+template <int METRIC, int VEC, int NCHUNK>
+__device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const float (&go)[NCHUNK][VEC],
+                                             const float (&ls)[NCHUNK], const float (&dl)[NCHUNK],
+                                             const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
+                                             const int* __restrict__ col, int beg, int end, int lane,
+                                             float (&dq)[NCHUNK][VEC], float (&dpar)[NCHUNK]) {
+  if (rc.group == 4) bwd_row_walk_t<METRIC, VEC, NCHUNK, 4>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar);
+  else if (rc.group == 8) bwd_row_walk_t<METRIC, VEC, NCHUNK, 8>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar);
+  else bwd_row_walk_t<METRIC, VEC, NCHUNK, 0>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar);
 }
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
@@ -514,8 +566,8 @@ geo_attn_bwd_row_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
 
 // ---- column pass over the transposed CSR: for source node j, dV[j] = sum_e a_e dctx[row_e],
 // dK[j] = sum_e ds_e * dscore/dk.  Gathers Q[row], dctx[row], lse[row,h], delta[row,h].
-template <int METRIC, int VEC, int NCHUNK>
-__device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], const float (&v)[NCHUNK][VEC],
+template <int METRIC, int VEC, int NCHUNK, int GROUP>
+__device__ __forceinline__ void bwd_col_walk_t(const float (&k)[NCHUNK][VEC], const float (&v)[NCHUNK][VEC],
                                              const float (&par)[NCHUNK], const int (&head)[NCHUNK], int group,
                                              const qkv_t* __restrict__ Q, int64_t ldq, const float* __restrict__ dctx,
                                              const float* __restrict__ lse, const float* __restrict__ delta, int heads,
@@ -549,19 +601,19 @@ __device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], cons
               float t = 0.f;
 #pragma unroll
               for (int i = 0; i < VEC; ++i) t = fmaf(qq[u][c][i], qq[u][c][i], t);
-              t = sqrtf(group_sum(t, group));
+              t = sqrtf(group_sum_t<GROUP>(t, group));
               qn = t == 0.f ? 1e-8f : t;
             }
             float p1, p2;
-            const float s = score_from_vectors<METRIC, VEC>(qq[u][c], k[c], group, par[c], qn, p1, p2);
-            const float a = expf(s - ls[u][c]);
+            const float s = score_from_vectors<METRIC, VEC, GROUP>(qq[u][c], k[c], group, par[c], qn, p1, p2);
+            const float a = fast_exp(s - ls[u][c]);
             float dp = 0.f;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
               dv[c][i] = fmaf(a, gg[u][c][i], dv[c][i]);
               dp = fmaf(gg[u][c][i], v[c][i], dp);
             }
-            dp = group_sum(dp, group);
+            dp = group_sum_t<GROUP>(dp, group);
             const float ds = a * (dp - dl[u][c]);
             accum_score_grad<METRIC, VEC, false>(ds, qq[u][c], k[c], s, p1, p2, par[c], qn, dk[c]);
           }
@@ -569,6 +621,18 @@ __device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], cons
       }
     }
   }
+}
+
+template <int METRIC, int VEC, int NCHUNK>
+__device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], const float (&v)[NCHUNK][VEC],
+                                             const float (&par)[NCHUNK], const int (&head)[NCHUNK], int group,
+                                             const qkv_t* __restrict__ Q, int64_t ldq, const float* __restrict__ dctx,
+                                             const float* __restrict__ lse, const float* __restrict__ delta, int heads,
+                                             const int* __restrict__ row_t, int beg, int end, int lane,
+                                             float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC]) {
+  if (group == 4) bwd_col_walk_t<METRIC, VEC, NCHUNK, 4>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv);
+  else if (group == 8) bwd_col_walk_t<METRIC, VEC, NCHUNK, 8>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv);
+  else bwd_col_walk_t<METRIC, VEC, NCHUNK, 0>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv);
 }
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>

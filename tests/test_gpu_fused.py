@@ -340,11 +340,12 @@ def test_layer_fused_equals_unfused(dev, n, t, hidden, heads):
     for a, b in zip(res[True][1], res[False][1]):
         _gclose(a, b)
     assert res[True][2].keys() == res[False][2].keys()
-    # analytically zero by softmax shift invariance (both sides hold rounding noise only): atol 1e-4
+    # analytically zero by softmax shift invariance: both sides hold only the rounding noise of a sum over n*t*heads terms
+    # of magnitude ~1 (measured 1.2e-4 for one element once kernel (a) moved to the SFU exp / sqrt): atol 5e-4
     zero = ("temporal_attention.k_linear.bias", "temporal_attention.time_q_proj.bias",
             "temporal_attention.time_encoding.basis_proj.bias")
     for k in res[True][2]:
         if k in zero:
-            torch.testing.assert_close(res[True][2][k], res[False][2][k], rtol=1e-4, atol=1e-4, msg=lambda m, k=k: f"d{k}: {m}")
+            torch.testing.assert_close(res[True][2][k], res[False][2][k], rtol=1e-4, atol=5e-4, msg=lambda m, k=k: f"d{k}: {m}")
         else:
             _gclose(res[True][2][k], res[False][2][k], msg=lambda m, k=k: f"d{k}: {m}")
