@@ -93,6 +93,12 @@ int tagan_csr_build_part(const int64_t* edge_index, int64_t num_edges, int32_t n
                          int32_t* status, void* workspace, size_t workspace_bytes,
                          tagan_stream_t stream);
 
+/* Profiling knob (synchronous; default 1): kernel (a) loads the gathered K / V / Q / dctx rows with an L2 evict_last
+ * policy and streams its own rows, results and gradients with evict_first, so a snapshot's K|V stay L2-resident while the
+ * kernel walks it; 0 switches the hints off.  The `_bf16` variant sets the bf16-storage build. */
+int tagan_geo_attn_set_l2_policy(int32_t mode);
+int tagan_geo_attn_set_l2_policy_bf16(int32_t mode);
+
 /* ---------------------------------------------------------------------------------------
  * (a2-a4) fused geometric attention over the CSR: per-entry per-head score from the
  * DistanceMetric, segment softmax over each row, weighted aggregation of V.  One warp per

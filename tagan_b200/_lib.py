@@ -69,6 +69,8 @@ SIGNATURES = {
     "tagan_gemm_tn_colsum": (_i32, [_i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _sz, _p]),
     "tagan_gemm_fused_workspace_bytes": (_sz, [_i32, _i64, _i64, _i64]),
     "tagan_gemm_set_tuning": (None, [_i32, _i32]),
+    "tagan_geo_attn_set_l2_policy": (_i32, [_i32]),
+    "tagan_geo_attn_set_l2_policy_bf16": (_i32, [_i32]),
     "tagan_gemm_set_trace": (None, [_p]),
     "tagan_gemm_fused": (_i32, [_i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p, C.POINTER(Epilogue), _i32,
                                 _p, _sz, _p]),

@@ -186,6 +186,79 @@ __device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const __nv_b
 }
 #endif
 
+// ---- L2 residency hints.  At config 3 one snapshot's K|V (100 MB) competes for the L2 with the kernel's own streams (Q rows,
+// ctx / gradient rows, column ids: another ~115 MB per snapshot) and the gathers hit only 52 % of the time (ncu).  With mode 1
+// the gathered rows are loaded with an evict_last policy and the streamed rows / results with evict_first
+// (createpolicy + .L2::cache_hint: the policy rides in the instruction's descriptor, no extra instructions per access).
+__constant__ int c_l2_mode = 1;
+struct L2Policies { uint64_t keep, stream; };
+__device__ __forceinline__ L2Policies make_l2_policies() {
+  L2Policies p;
+  if (c_l2_mode == 1) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  } else {
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.keep));
+    p.stream = p.keep;
+  }
+  return p;
+}
+template <int VEC> struct HintIO;
+template <> struct HintIO<1> {
+  static __device__ __forceinline__ void load(float* d, const float* p, uint64_t pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(d[0]) : "l"(p), "l"(pol));
+  }
+  static __device__ __forceinline__ void store(float* p, const float* s, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(s[0]), "l"(pol) : "memory");
+  }
+};
+template <> struct HintIO<2> {
+  static __device__ __forceinline__ void load(float* d, const float* p, uint64_t pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(d[0]), "=f"(d[1]) : "l"(p), "l"(pol));
+  }
+  static __device__ __forceinline__ void store(float* p, const float* s, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(s[0]), "f"(s[1]), "l"(pol) : "memory");
+  }
+};
+template <> struct HintIO<4> {
+  static __device__ __forceinline__ void load(float* d, const float* p, uint64_t pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "l"(p), "l"(pol));
+  }
+  static __device__ __forceinline__ void store(float* p, const float* s, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]), "l"(pol) : "memory");
+  }
+};
+template <int VEC, int NCHUNK>
+__device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const float* base, int lane, uint64_t pol) {
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) HintIO<VEC>::load(dst[c], base + c * 32 * VEC + lane * VEC, pol);
+}
+#ifdef TAGAN_GEO_BF16
+template <int VEC, int NCHUNK>
+__device__ __forceinline__ void load_row(float (&dst)[NCHUNK][VEC], const __nv_bfloat16* base, int lane, uint64_t pol) {
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    const __nv_bfloat16* p = base + c * 32 * VEC + lane * VEC;
+    if (VEC == 4) {
+      uint32_t x, y;
+      asm volatile("ld.global.nc.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;" : "=r"(x), "=r"(y) : "l"(p), "l"(pol));
+      dst[c][0] = bf16_bits_to_float(x & 0xffffu); dst[c][1 % VEC] = bf16_bits_to_float(x >> 16);
+      dst[c][2 % VEC] = bf16_bits_to_float(y & 0xffffu); dst[c][3 % VEC] = bf16_bits_to_float(y >> 16);
+    } else if (VEC == 2) {
+      uint32_t x;
+      asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(x) : "l"(p), "l"(pol));
+      dst[c][0] = bf16_bits_to_float(x & 0xffffu); dst[c][1 % VEC] = bf16_bits_to_float(x >> 16);
+    } else {
+      unsigned short x;
+      asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(x) : "l"(p), "l"(pol));
+      dst[c][0] = bf16_bits_to_float((uint32_t)x);
+    }
+  }
+}
+#endif
+
 // Rows (or, in the column pass, source nodes) with more than HEAVY_THRESH entries are "heavy": the
 // warp-per-row kernels skip them and a second launch gives each of them a whole CTA -- its 8 warps take
 // contiguous slices of the entries and their partial states are merged through shared memory in warp
@@ -235,9 +308,9 @@ struct RowCtx {
 
 template <int METRIC, int VEC, int NCHUNK>
 __device__ __forceinline__ void init_row(RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* qrow, const float* metric_param,
-                                         int D, int lane) {
+                                         int D, int lane, uint64_t pol) {
   rc.group = D / VEC;
-  load_row<VEC, NCHUNK>(rc.q, qrow, lane);
+  load_row<VEC, NCHUNK>(rc.q, qrow, lane, pol);
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
     rc.head[c] = (c * 32 * VEC + lane * VEC) / D;
@@ -259,7 +332,7 @@ template <int METRIC, int VEC, int NCHUNK, int GROUP>
 __device__ __forceinline__ void fwd_walk_t(const RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* __restrict__ K,
                                            const qkv_t* __restrict__ V, int64_t ld, const int* __restrict__ col, int beg,
                                            int end, int lane, float (&m)[NCHUNK], float (&l)[NCHUNK],
-                                           float (&acc)[NCHUNK][VEC]) {
+                                           float (&acc)[NCHUNK][VEC], uint64_t pk) {
   constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
   for (int base = beg; base < end; base += 32) {
     const int n = min(32, end - base);
@@ -269,8 +342,8 @@ __device__ __forceinline__ void fwd_walk_t(const RowCtx<METRIC, VEC, NCHUNK>& rc
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int cj = __shfl_sync(FULL_MASK, mycol, min(j + u, n - 1));
-        load_row<VEC, NCHUNK>(kk[u], K + (int64_t)cj * ld, lane);
-        load_row<VEC, NCHUNK>(vv[u], V + (int64_t)cj * ld, lane);
+        load_row<VEC, NCHUNK>(kk[u], K + (int64_t)cj * ld, lane, pk);
+        load_row<VEC, NCHUNK>(vv[u], V + (int64_t)cj * ld, lane, pk);
       }
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
@@ -303,10 +376,10 @@ template <int METRIC, int VEC, int NCHUNK>
 __device__ __forceinline__ void fwd_walk(const RowCtx<METRIC, VEC, NCHUNK>& rc, const qkv_t* __restrict__ K,
                                          const qkv_t* __restrict__ V, int64_t ld, const int* __restrict__ col, int beg,
                                          int end, int lane, float (&m)[NCHUNK], float (&l)[NCHUNK],
-                                         float (&acc)[NCHUNK][VEC]) {
-  if (rc.group == 4) fwd_walk_t<METRIC, VEC, NCHUNK, 4>(rc, K, V, ld, col, beg, end, lane, m, l, acc);
-  else if (rc.group == 8) fwd_walk_t<METRIC, VEC, NCHUNK, 8>(rc, K, V, ld, col, beg, end, lane, m, l, acc);
-  else fwd_walk_t<METRIC, VEC, NCHUNK, 0>(rc, K, V, ld, col, beg, end, lane, m, l, acc);
+                                         float (&acc)[NCHUNK][VEC], uint64_t pk) {
+  if (rc.group == 4) fwd_walk_t<METRIC, VEC, NCHUNK, 4>(rc, K, V, ld, col, beg, end, lane, m, l, acc, pk);
+  else if (rc.group == 8) fwd_walk_t<METRIC, VEC, NCHUNK, 8>(rc, K, V, ld, col, beg, end, lane, m, l, acc, pk);
+  else fwd_walk_t<METRIC, VEC, NCHUNK, 0>(rc, K, V, ld, col, beg, end, lane, m, l, acc, pk);
 }
 
 template <int METRIC, int VEC, int NCHUNK>
@@ -334,6 +407,7 @@ geo_attn_fwd_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __res
                     float* __restrict__ attn) {
   constexpr int H = 32 * VEC * NCHUNK;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const L2Policies pol = make_l2_policies();
   auto finish = [&](const RowCtx<METRIC, VEC, NCHUNK>& rc, int row, const float (&m)[NCHUNK], const float (&l)[NCHUNK],
                     const float (&acc)[NCHUNK][VEC], float (&lse_c)[NCHUNK]) {
 #pragma unroll
@@ -342,7 +416,7 @@ geo_attn_fwd_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __res
       float o[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) o[i] = acc[c][i] * inv;
-      VecIO<VEC>::store(ctx + (int64_t)row * H + c * 32 * VEC + lane * VEC, o);
+      HintIO<VEC>::store(ctx + (int64_t)row * H + c * 32 * VEC + lane * VEC, o, pol.stream);
       lse_c[c] = m[c] + logf(l[c]);
       if ((lane & (rc.group - 1)) == 0) lse[(int64_t)row * heads + rc.head[c]] = lse_c[c];   // group leader
     }
@@ -353,7 +427,7 @@ geo_attn_fwd_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __res
     const int beg = rowptr[row], end = rowptr[row + 1];
     if (end - beg > HEAVY_THRESH) return;
     RowCtx<METRIC, VEC, NCHUNK> rc;
-    init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane);
+    init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane, pol.stream);
     float m[NCHUNK], l[NCHUNK], acc[NCHUNK][VEC], lse_c[NCHUNK];
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
@@ -361,7 +435,7 @@ geo_attn_fwd_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __res
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[c][i] = 0.f;
     }
-    fwd_walk<METRIC, VEC, NCHUNK>(rc, K, V, ld, col, beg, end, lane, m, l, acc);
+    fwd_walk<METRIC, VEC, NCHUNK>(rc, K, V, ld, col, beg, end, lane, m, l, acc, pol.keep);
     finish(rc, row, m, l, acc, lse_c);
     if (attn != nullptr) fwd_attn_pass<METRIC, VEC, NCHUNK>(rc, K, ld, col, beg, end, lane, heads, lse_c, attn);
   } else {
@@ -373,7 +447,7 @@ geo_attn_fwd_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __res
       int b, e;
       warp_slice(beg, end, w, b, e);
       RowCtx<METRIC, VEC, NCHUNK> rc;
-      init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane);
+      init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane, pol.stream);
       float m[NCHUNK], l[NCHUNK], acc[NCHUNK][VEC], lse_c[NCHUNK];
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
@@ -381,7 +455,7 @@ geo_attn_fwd_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __res
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[c][i] = 0.f;
       }
-      fwd_walk<METRIC, VEC, NCHUNK>(rc, K, V, ld, col, b, e, lane, m, l, acc);
+      fwd_walk<METRIC, VEC, NCHUNK>(rc, K, V, ld, col, b, e, lane, m, l, acc, pol.keep);
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
         sm_m[w][c][lane] = m[c]; sm_l[w][c][lane] = l[c];
@@ -427,7 +501,7 @@ __device__ __forceinline__ void bwd_row_walk_t(const RowCtx<METRIC, VEC, NCHUNK>
                                              const float (&ls)[NCHUNK], const float (&dl)[NCHUNK],
                                              const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
                                              const int* __restrict__ col, int beg, int end, int lane,
-                                             float (&dq)[NCHUNK][VEC], float (&dpar)[NCHUNK]) {
+                                             float (&dq)[NCHUNK][VEC], float (&dpar)[NCHUNK], uint64_t pk) {
   constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
   for (int base = beg; base < end; base += 32) {
     const int n = min(32, end - base);
@@ -437,8 +511,8 @@ __device__ __forceinline__ void bwd_row_walk_t(const RowCtx<METRIC, VEC, NCHUNK>
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int cj = __shfl_sync(FULL_MASK, mycol, min(j + u, n - 1));
-        load_row<VEC, NCHUNK>(kk[u], K + (int64_t)cj * ld, lane);
-        load_row<VEC, NCHUNK>(vv[u], V + (int64_t)cj * ld, lane);
+        load_row<VEC, NCHUNK>(kk[u], K + (int64_t)cj * ld, lane, pk);
+        load_row<VEC, NCHUNK>(vv[u], V + (int64_t)cj * ld, lane, pk);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -466,10 +540,10 @@ __device__ __forceinline__ void bwd_row_walk(const RowCtx<METRIC, VEC, NCHUNK>& 
                                              const float (&ls)[NCHUNK], const float (&dl)[NCHUNK],
                                              const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
                                              const int* __restrict__ col, int beg, int end, int lane,
-                                             float (&dq)[NCHUNK][VEC], float (&dpar)[NCHUNK]) {
-  if (rc.group == 4) bwd_row_walk_t<METRIC, VEC, NCHUNK, 4>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar);
-  else if (rc.group == 8) bwd_row_walk_t<METRIC, VEC, NCHUNK, 8>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar);
-  else bwd_row_walk_t<METRIC, VEC, NCHUNK, 0>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar);
+                                             float (&dq)[NCHUNK][VEC], float (&dpar)[NCHUNK], uint64_t pk) {
+  if (rc.group == 4) bwd_row_walk_t<METRIC, VEC, NCHUNK, 4>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar, pk);
+  else if (rc.group == 8) bwd_row_walk_t<METRIC, VEC, NCHUNK, 8>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar, pk);
+  else bwd_row_walk_t<METRIC, VEC, NCHUNK, 0>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar, pk);
 }
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
@@ -481,13 +555,14 @@ geo_attn_bwd_row_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
                         int64_t ldd, float* __restrict__ delta, float* __restrict__ dparam_rows) {
   constexpr int H = 32 * VEC * NCHUNK;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const L2Policies pol = make_l2_policies();
   // per-row prologue shared by both modes: q, dctx row, lse, delta = dctx . ctx
   auto prologue = [&](int row, RowCtx<METRIC, VEC, NCHUNK>& rc, float (&go)[NCHUNK][VEC], float (&ls)[NCHUNK],
                       float (&dl)[NCHUNK], bool write_delta) {
-    init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane);
-    load_row<VEC, NCHUNK>(go, dctx + (int64_t)row * H, lane);
+    init_row<METRIC, VEC, NCHUNK>(rc, Q + (int64_t)row * ldq, metric_param, D, lane, pol.stream);
+    load_row<VEC, NCHUNK>(go, dctx + (int64_t)row * H, lane, pol.stream);
     float cx[NCHUNK][VEC];
-    load_row<VEC, NCHUNK>(cx, ctx + (int64_t)row * H, lane);
+    load_row<VEC, NCHUNK>(cx, ctx + (int64_t)row * H, lane, pol.stream);
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
       float t = 0.f;
@@ -501,7 +576,7 @@ geo_attn_bwd_row_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
   auto store = [&](const RowCtx<METRIC, VEC, NCHUNK>& rc, int row, const float (&dq)[NCHUNK][VEC], const float (&dpar)[NCHUNK]) {
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
-      VecIO<VEC>::store(dQ + (int64_t)row * ldd + c * 32 * VEC + lane * VEC, dq[c]);
+      HintIO<VEC>::store(dQ + (int64_t)row * ldd + c * 32 * VEC + lane * VEC, dq[c], pol.stream);
       if (MetricTraits<METRIC>::kParam && dparam_rows != nullptr && (lane & (rc.group - 1)) == 0)
         dparam_rows[(int64_t)row * heads + rc.head[c]] = dpar[c];
     }
@@ -520,7 +595,7 @@ geo_attn_bwd_row_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
 #pragma unroll
       for (int i = 0; i < VEC; ++i) dq[c][i] = 0.f;
     }
-    bwd_row_walk<METRIC, VEC, NCHUNK>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar);
+    bwd_row_walk<METRIC, VEC, NCHUNK>(rc, go, ls, dl, K, V, ld, col, beg, end, lane, dq, dpar, pol.keep);
     store(rc, row, dq, dpar);
   } else {
     __shared__ float sm_dq[WARPS_PER_BLOCK][NCHUNK][VEC][32];
@@ -538,7 +613,7 @@ geo_attn_bwd_row_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
 #pragma unroll
         for (int i = 0; i < VEC; ++i) dq[c][i] = 0.f;
       }
-      bwd_row_walk<METRIC, VEC, NCHUNK>(rc, go, ls, dl, K, V, ld, col, b, e, lane, dq, dpar);
+      bwd_row_walk<METRIC, VEC, NCHUNK>(rc, go, ls, dl, K, V, ld, col, b, e, lane, dq, dpar, pol.keep);
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
         sm_dp[w][c][lane] = dpar[c];
@@ -572,7 +647,7 @@ __device__ __forceinline__ void bwd_col_walk_t(const float (&k)[NCHUNK][VEC], co
                                              const qkv_t* __restrict__ Q, int64_t ldq, const float* __restrict__ dctx,
                                              const float* __restrict__ lse, const float* __restrict__ delta, int heads,
                                              const int* __restrict__ row_t, int beg, int end, int lane,
-                                             float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC]) {
+                                             float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC], uint64_t pk) {
   constexpr int U = (VEC * NCHUNK >= 8) ? 2 : 4;
   constexpr int H = 32 * VEC * NCHUNK;
   for (int base = beg; base < end; base += 32) {
@@ -583,8 +658,8 @@ __device__ __forceinline__ void bwd_col_walk_t(const float (&k)[NCHUNK][VEC], co
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int r = __shfl_sync(FULL_MASK, myrow, min(j + u, n - 1));
-        load_row<VEC, NCHUNK>(qq[u], Q + (int64_t)r * ldq, lane);
-        load_row<VEC, NCHUNK>(gg[u], dctx + (int64_t)r * H, lane);
+        load_row<VEC, NCHUNK>(qq[u], Q + (int64_t)r * ldq, lane, pk);
+        load_row<VEC, NCHUNK>(gg[u], dctx + (int64_t)r * H, lane, pk);
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
           ls[u][c] = __ldg(lse + (int64_t)r * heads + head[c]);
@@ -629,10 +704,10 @@ __device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], cons
                                              const qkv_t* __restrict__ Q, int64_t ldq, const float* __restrict__ dctx,
                                              const float* __restrict__ lse, const float* __restrict__ delta, int heads,
                                              const int* __restrict__ row_t, int beg, int end, int lane,
-                                             float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC]) {
-  if (group == 4) bwd_col_walk_t<METRIC, VEC, NCHUNK, 4>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv);
-  else if (group == 8) bwd_col_walk_t<METRIC, VEC, NCHUNK, 8>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv);
-  else bwd_col_walk_t<METRIC, VEC, NCHUNK, 0>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv);
+                                             float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC], uint64_t pk) {
+  if (group == 4) bwd_col_walk_t<METRIC, VEC, NCHUNK, 4>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv, pk);
+  else if (group == 8) bwd_col_walk_t<METRIC, VEC, NCHUNK, 8>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv, pk);
+  else bwd_col_walk_t<METRIC, VEC, NCHUNK, 0>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv, pk);
 }
 
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
@@ -643,11 +718,12 @@ geo_attn_bwd_col_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
                         const float* __restrict__ delta, const float* __restrict__ dctx, float* __restrict__ dK,
                         float* __restrict__ dV, int64_t ldd) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const L2Policies pol = make_l2_policies();
   const int group = D / VEC;
   auto load_node = [&](int node, float (&k)[NCHUNK][VEC], float (&v)[NCHUNK][VEC], float (&par)[NCHUNK], int (&head)[NCHUNK],
                        float (&dk)[NCHUNK][VEC], float (&dv)[NCHUNK][VEC]) {
-    load_row<VEC, NCHUNK>(k, K + (int64_t)node * ld, lane);
-    load_row<VEC, NCHUNK>(v, V + (int64_t)node * ld, lane);
+    load_row<VEC, NCHUNK>(k, K + (int64_t)node * ld, lane, pol.stream);
+    load_row<VEC, NCHUNK>(v, V + (int64_t)node * ld, lane, pol.stream);
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
       head[c] = (c * 32 * VEC + lane * VEC) / D;
@@ -659,8 +735,8 @@ geo_attn_bwd_col_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
   auto store = [&](int node, const float (&dk)[NCHUNK][VEC], const float (&dv)[NCHUNK][VEC]) {
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
-      VecIO<VEC>::store(dK + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dk[c]);
-      VecIO<VEC>::store(dV + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dv[c]);
+      HintIO<VEC>::store(dK + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dk[c], pol.stream);
+      HintIO<VEC>::store(dV + (int64_t)node * ldd + c * 32 * VEC + lane * VEC, dv[c], pol.stream);
     }
   };
   if (!HEAVY) {
@@ -671,7 +747,7 @@ geo_attn_bwd_col_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
     float k[NCHUNK][VEC], v[NCHUNK][VEC], dk[NCHUNK][VEC], dv[NCHUNK][VEC], par[NCHUNK];
     int head[NCHUNK];
     load_node(node, k, v, par, head, dk, dv);
-    bwd_col_walk<METRIC, VEC, NCHUNK>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv);
+    bwd_col_walk<METRIC, VEC, NCHUNK>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv, pol.keep);
     store(node, dk, dv);
   } else {
     __shared__ float sm_dk[WARPS_PER_BLOCK][NCHUNK][VEC][32], sm_dv[WARPS_PER_BLOCK][NCHUNK][VEC][32];
@@ -682,7 +758,7 @@ geo_attn_bwd_col_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* _
       float k[NCHUNK][VEC], v[NCHUNK][VEC], dk[NCHUNK][VEC], dv[NCHUNK][VEC], par[NCHUNK];
       int head[NCHUNK];
       load_node(node, k, v, par, head, dk, dv);
-      bwd_col_walk<METRIC, VEC, NCHUNK>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, b, e, lane, dk, dv);
+      bwd_col_walk<METRIC, VEC, NCHUNK>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, b, e, lane, dk, dv, pol.keep);
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c)
 #pragma unroll
@@ -761,6 +837,12 @@ bool pick_shape(int H, int heads, Shape* s) {
   }
 
 }  // namespace
+
+/* 1 (default): gathered rows evict_last, streamed rows / results evict_first; 0: no L2 hints.  Synchronous (profiling knob). */
+TAGAN_API int GEO_NAME(tagan_geo_attn_set_l2_policy)(int32_t mode) {
+  const int m = mode ? 1 : 0;
+  return (int)cudaMemcpyToSymbol(c_l2_mode, &m, sizeof(int));
+}
 
 TAGAN_API int GEO_NAME(tagan_geo_attn_fwd_part)(const qkv_api_t* Q_, int64_t ldq, const qkv_api_t* K_, const qkv_api_t* V_, int64_t ldkv,
                                       const int32_t* rowptr, const int32_t* col, int32_t n_rows, int32_t H,
