@@ -16,6 +16,22 @@ static inline int tagan_launch_status() {
 
 static inline cudaStream_t as_stream(tagan_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE attribute of a kernel: remember the largest size
+// set per device ordinal (one instance per kernel / call site), so a process that drives several GPUs opts in on each.
+struct SmemOptIn {
+  size_t bytes[64] = {};
+  template <typename Kern>
+  cudaError_t ensure(Kern kern, size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+    if (dev >= 0 && bytes[dev] >= smem) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && dev >= 0) bytes[dev] = smem;
+    return e;
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);

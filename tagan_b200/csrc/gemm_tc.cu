@@ -436,11 +436,10 @@ size_t tagan_gemm_tc_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K
 int tagan_gemm_tc(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                   int64_t ldb, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t passes,
                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  static SmemOptIn opt_in;
+  {
+    const cudaError_t e = opt_in.ensure(gemm_tc_kernel, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   Plan pl = make_plan(M, N, K);
   Params p;

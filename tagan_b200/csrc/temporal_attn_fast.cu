@@ -437,11 +437,8 @@ void tattn_bwd_fast_launch_one(int grid, int threads, size_t smem, cudaStream_t 
                                const float* V, int64_t ld, int64_t B, int T, int heads, int64_t rsb, int64_t rst,
                                const float* bias, MaskSpec ms, const float* ctx, const float* lse, const float* dctx,
                                float* dQ, float* dK, float* dV, int64_t ldd, float* dbias_partial) {
-  static size_t opted = 0;                      // per instantiation; raising the limit is idempotent
-  if (smem > 48 * 1024 && smem > opted) {
-    cudaFuncSetAttribute(tattn_bwd_fast_kernel<D, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    opted = smem;
-  }
+  static SmemOptIn opt_in;                      // per instantiation and device
+  opt_in.ensure(tattn_bwd_fast_kernel<D, TP>, smem);
   tattn_bwd_fast_kernel<D, TP><<<grid, threads, smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, ms, ctx, lse, dctx,
                                                            dQ, dK, dV, ldd, dbias_partial);
 }
@@ -480,26 +477,18 @@ bool tagan_tattn_bwd_fast_launch(int D, int TP, int grid, int threads, size_t sm
 // ---- tensor-core kernels: 8 < T <= 16, D in {16, 32}, heads <= 8, bias shared by all nodes ----
 static size_t mma_fwd_smem(int D, int heads) { return (size_t)heads * (3 * 16 * (D + 4) + 16) * sizeof(float); }
 
-template <typename Kern>
-static bool opt_in_smem(Kern kern, size_t smem, size_t* opted) {
-  if (smem > 48 * 1024 && smem > *opted) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-    *opted = smem;
-  }
-  return true;
-}
 
 bool tagan_tattn_fwd_mma_launch(int D, int grid, cudaStream_t st, const float* Q, const float* K, const float* V, int64_t ld,
                                 int64_t B, int T, int heads, int64_t rsb, int64_t rst, const float* bias, MaskSpec ms,
                                 float* ctx, float* lse, float* attn) {
   if (T <= 8 || T > 16 || heads > 8 || (D != 16 && D != 32)) return false;
   const size_t smem = mma_fwd_smem(D, heads);
-  static size_t opted16 = 0, opted32 = 0;
+  static SmemOptIn opted16, opted32;
   if (D == 16) {
-    if (!opt_in_smem(tattn_fwd_mma_kernel<16>, smem, &opted16)) return false;
+    if (opted16.ensure(tattn_fwd_mma_kernel<16>, smem) != cudaSuccess) return false;
     tattn_fwd_mma_kernel<16><<<grid, heads * 32, smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, ms, ctx, lse, attn);
   } else {
-    if (!opt_in_smem(tattn_fwd_mma_kernel<32>, smem, &opted32)) return false;
+    if (opted32.ensure(tattn_fwd_mma_kernel<32>, smem) != cudaSuccess) return false;
     tattn_fwd_mma_kernel<32><<<grid, heads * 32, smem, st>>>(Q, K, V, ld, B, T, heads, rsb, rst, bias, ms, ctx, lse, attn);
   }
   return true;
