@@ -183,6 +183,7 @@ struct Params {
   long long* trace;         // debug: CTA 0 writes clock64() stamps of its first TRACE_N k-blocks / tiles ([8][TRACE_N]) or null
   int prefetch;             // the TMA producer asks L2 for the streamed operand tiles this many k-blocks ahead of the smem ring
                             // (the ring holds 4 x 16 KB per operand per SM: too few bytes in flight to cover HBM latency)
+  int st256;                // interior plain stores as 256-bit STG (C and bias 32-byte aligned, ldc % 8 == 0)
   uint32_t ticks;           // suspend-time hint of every mbarrier wait (0 = plain try_wait polling)
   int epi_pipe;             // epilogue: issue the TMEM load of chunk cc+1 before the read-back / stores of chunk cc
   int early_release;        // resident mode: the A smem slot is released by the split warps, the A TMEM slot by the MMA commit
@@ -802,7 +803,26 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         __syncwarp();
         const int64_t c0 = n0 + cc * 32 + (lane & 7) * 4;
         const uint32_t src0 = stg + (uint32_t)(((lane >> 3) * EPI_PITCH + (lane & 7) * 4) * 4);
-        if (interior) {
+        if (interior && p.st256 && !rmw) {
+          // 256-bit stores (sm_100 STG.256): lane = row (lane >> 2) + 8 i, columns 8 (lane & 3) .. +7 -- half as many store
+          // instructions per chunk as the 128-bit form below
+          const int64_t c8 = n0 + cc * 32 + (lane & 3) * 8;
+          float4 b4a = make_float4(0.f, 0.f, 0.f, 0.f), b4b = b4a;
+          if (bias_vec) { b4a = __ldg(reinterpret_cast<const float4*>(p.bias + c8)); b4b = __ldg(reinterpret_cast<const float4*>(p.bias + c8 + 4)); }
+          const uint32_t srow = stg + (uint32_t)((((lane >> 2) * EPI_PITCH) + (lane & 3) * 8) * 4);
+          float* orow = out + ((int64_t)mt * BM + warp * 32 + (lane >> 2)) * ldo + c8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 a = lds128(srow + (uint32_t)(i * 8 * EPI_PITCH * 4));
+            float4 b = lds128(srow + (uint32_t)(i * 8 * EPI_PITCH * 4 + 16));
+            a.x += b4a.x; a.y += b4a.y; a.z += b4a.z; a.w += b4a.w;
+            b.x += b4b.x; b.y += b4b.y; b.z += b4b.z; b.w += b4b.w;
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         ::"l"(orow + (int64_t)(i * 8) * ldo), "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)),
+                           "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)),
+                           "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)) : "memory");
+          }
+        } else if (interior) {
           // whole tile inside the matrix, 16-byte aligned rows, plain store: straight-line code
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias_vec) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
@@ -1037,6 +1057,7 @@ bool tagan_gemm_tma_supported(int64_t M, int64_t N, int64_t K, const float* A, i
   return get_encode() != nullptr;
 }
 
+static int g_st256 = 1;
 static int g_b_resident = 1, g_prefetch = 0, g_epi_pipe = 0, g_early_release = 0, g_wait_ticks = 0x989680;
 void tagan_gemm_tma_set_tuning(int key, int value) {
   if (key == 0) g_b_resident = value;
@@ -1044,6 +1065,7 @@ void tagan_gemm_tma_set_tuning(int key, int value) {
   else if (key == 2) g_epi_pipe = value;
   else if (key == 3) g_early_release = value;
   else if (key == 4) g_wait_ticks = value;
+  else if (key == 5) g_st256 = value;
 }
 static long long* g_trace = nullptr;
 void tagan_gemm_tma_set_trace(void* buf) { g_trace = static_cast<long long*>(buf); }
@@ -1083,6 +1105,13 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   p.fused = 0;
   p.K1 = 0;
   p.epi = tagan_epilogue{};
+  // a STORE epilogue without extra inputs / outputs is the plain epilogue writing to out0 (resident weights, 256-bit stores)
+  if (epi != nullptr && epi->mode == TAGAN_EPI_STORE && epi->in0 == nullptr && epi->in1 == nullptr && epi->out1 == nullptr &&
+      epi->out2 == nullptr && op != 2 && pl.splits == 1 && colsum_a == nullptr && !accumulate) {
+    C = epi->out0;
+    ldc = epi->ld_out0;
+    epi = nullptr;
+  }
   if (epi != nullptr) {
     if (op == 2 || pl.splits != 1 || colsum_a != nullptr || accumulate) return TAGAN_E_UNSUPPORTED;
     if (epi->mode == TAGAN_EPI_RES_LN && epi->gamma != nullptr && pl.tiles_n != 1) return TAGAN_E_UNSUPPORTED;
@@ -1155,6 +1184,8 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   p.prefetch = g_prefetch;
   p.epi_pipe = g_epi_pipe;
   p.ticks = (uint32_t)g_wait_ticks;
+  p.st256 = (g_st256 && p.partial == nullptr && (reinterpret_cast<uintptr_t>(C) & 31) == 0 && (ldc % 8) == 0 &&
+             (reinterpret_cast<uintptr_t>(bias) & 31) == 0) ? 1 : 0;
   p.early_release = 0;
   p.trace = g_trace;
   p.b_resident = 0;
