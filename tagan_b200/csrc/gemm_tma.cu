@@ -464,6 +464,9 @@ __device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int la
   if (lane == 0) mbar_arrive(tmem_empty_bar);
 }
 
+// FUSED = false leaves the fused epilogues (struct tagan_epilogue modes) out of the instantiation: the plain projections are
+// sensitive to the register allocation of the epilogue role, and the fused code paths are what pushes it into spills
+template <bool FUSED>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmA2) {
@@ -762,7 +765,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
       mbar_wait_t(p.ticks, &tmem_full[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 0) TRACE(6, tr_tile);
-      if (p.fused) {                                       // warp-uniform
+      if (FUSED && p.fused) {                              // warp-uniform
         if (p.fused == 2) epilogue_fused<true>(p, warp, lane, acc, mt, n0, epi_u32, &tmem_empty[acc]);
         else epilogue_fused<false>(p, warp, lane, acc, mt, n0, epi_u32, &tmem_empty[acc]);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -1096,7 +1099,9 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
   if (dev < 0 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0) attr_set[dev] = true;
   }
@@ -1194,7 +1199,8 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
     p.early_release = g_early_release;
     grid = 148 / pl.tiles_n * pl.tiles_n;
   }
-  gemm_tma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  if (p.fused) gemm_tma_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  else gemm_tma_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
   if (p.partial)
     tma_splitk_reduce<<<ceil_div_i64(M * N, 32), 256, 0, st>>>(p.partial, pl.parts, M, N, bias, C, ldc, accumulate);
   if (p.colsum_part)
