@@ -713,8 +713,10 @@ __device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], cons
   else bwd_col_walk_t<METRIC, VEC, NCHUNK, 0>(k, v, par, head, group, Q, ldq, dctx, lse, delta, heads, row_t, beg, end, lane, dk, dv, pk);
 }
 
+// the column pass keeps two gathered rows per entry plus dK and dV: at 4 CTAs per SM (64 registers) it spills
+constexpr int min_ctas_col(int vec, int nchunk) { return vec * nchunk >= 8 ? 2 : 3; }
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas(VEC, NCHUNK))
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas_col(VEC, NCHUNK))
 geo_attn_bwd_col_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
                         const int* __restrict__ rowptr_t, const int* __restrict__ row_t, int N, int heads, int D,
                         const float* __restrict__ metric_param, const float* __restrict__ lse,
