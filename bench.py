@@ -623,7 +623,10 @@ def run_ours(args):
     if os.path.exists(traffic_file):
         try:
             tr = json.load(open(traffic_file)).get(args.workload, {})
-            roofline["traffic"] = tr.get("geo_attn_bwd")
+            per_snap = tr.get("geo_attn_bwd_per_snapshot")
+            roofline["traffic"] = per_snap * snaps_bwd if per_snap is not None else tr.get("geo_attn_bwd")
+            if tr.get("geo_attn_fwd_per_snapshot") is not None:
+                roofline["geo_attn_fwd"]["traffic"] = tr["geo_attn_fwd_per_snapshot"] * snaps_fwd
             roofline["traffic_source"] = tr.get("source", "profiles/traffic.json (ncu --set full, dram__bytes_read+write per launch)")
         except Exception:
             pass
