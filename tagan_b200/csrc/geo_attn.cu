@@ -714,7 +714,7 @@ __device__ __forceinline__ void bwd_col_walk(const float (&k)[NCHUNK][VEC], cons
 }
 
 // the column pass keeps two gathered rows per entry plus dK and dV: at 4 CTAs per SM (64 registers) it spills
-constexpr int min_ctas_col(int vec, int nchunk) { return vec * nchunk >= 8 ? 2 : 3; }
+constexpr int min_ctas_col(int vec, int nchunk) { return vec * nchunk >= 16 ? 2 : 3; }   // H = 256 / 512 as before
 template <int METRIC, int VEC, int NCHUNK, bool HEAVY>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, min_ctas_col(VEC, NCHUNK))
 geo_attn_bwd_col_kernel(const qkv_t* __restrict__ Q, int64_t ldq, const qkv_t* __restrict__ K, const qkv_t* __restrict__ V, int64_t ld,
