@@ -32,3 +32,15 @@ def test_model_state_dict_keys_match_reference_golden(golden):
         res = m.load_state_dict(c["sd"])
         assert not res.missing_keys and not res.unexpected_keys
         assert set(dict(m.named_parameters())) == set(c["grads"])
+
+
+def test_batched_csr_has_no_cpu_path():
+    """The block-diagonal CSR build, like every product entry point, refuses host tensors instead of falling back."""
+    import pytest
+    import torch
+    from tagan_b200 import ops
+    eis = [torch.randint(0, 5, (2, 7)), torch.randint(0, 4, (2, 3))]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.build_csr_batched(eis, [5, 4])
+    with pytest.raises(ValueError):
+        ops.build_csr_batched([], [])
