@@ -147,7 +147,7 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, i
 }
 
 constexpr int TRACE_N = 512;
-#define TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < TRACE_N) p.trace[(slot) * TRACE_N + (idx)] = clock64(); } while (0)
+#define TRACE(slot, idx) do { if (trace_buf != nullptr && blockIdx.x == 0 && (idx) < TRACE_N) trace_buf[(slot) * TRACE_N + (idx)] = clock64(); } while (0)
 
 // one 32-column chunk of the accumulator: lane = row, r[j] = column j of the chunk (asynchronous: tcgen05.wait::ld before use)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -466,7 +466,10 @@ __device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int la
 
 // FUSED = false leaves the fused epilogues (struct tagan_epilogue modes) out of the instantiation: the plain projections are
 // sensitive to the register allocation of the epilogue role, and the fused code paths are what pushes it into spills
-template <bool FUSED>
+// SIMPLE = the shape of almost every projection of a step (pre-split K-major weights, no split-K, plain store, no profiling
+// knobs): the instantiation drops the MN-major / in-kernel-split / split-K / trace / prefetch code, which leaves a kernel a
+// quarter of the general one's size.
+template <bool FUSED, bool SIMPLE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmA2) {
@@ -483,6 +486,17 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
   const uint32_t epi_u32 = smem_u32(smem + (size_t)STAGES * STAGE_BYTES);      // 1024-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool a_mn = SIMPLE ? false : p.a_mn_major != 0;
+  const bool b_mn = SIMPLE ? false : p.b_mn_major != 0;
+  const bool b_pre = SIMPLE ? true : p.b_presplit != 0;
+  float* const colsum_part = SIMPLE ? nullptr : p.colsum_part;
+  float* const partial = SIMPLE ? nullptr : p.partial;
+  const int cta_acc = SIMPLE ? 0 : p.cta_acc;
+  const int accum_c = SIMPLE ? 0 : p.accumulate;
+  const int pf_dist = SIMPLE ? 0 : p.prefetch;
+  const bool early_rel = SIMPLE ? false : p.early_release != 0;
+  const bool epi_pipe_on = SIMPLE ? false : p.epi_pipe != 0;
+  long long* const trace_buf = SIMPLE ? nullptr : p.trace;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_bar[s], 1); mbar_init(&full_bar[s], SPLIT_WARPS); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
@@ -520,7 +534,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         mbar_arrive_expect_tx(bres_bar, (uint32_t)(nkb * 2 * TILE_BYTES));
         for (int kb = 0; kb < nkb; ++kb) {
           uint8_t* st = smem + (size_t)kb * STAGE_BYTES;
-          if (!p.b_mn_major) {
+          if (!b_mn) {
             tma_load_2d(st + TILE_BYTES, &tmB, kb * BK, n0, bres_bar);
             tma_load_2d(st + 2 * TILE_BYTES, &tmB2, kb * BK, n0, bres_bar);
           } else {
@@ -533,8 +547,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         }
       }
       int tr_kb = 0;
-      // L2 prefetch iterator: the same (work item, k-block) sequence, p.prefetch k-blocks ahead
-      const bool pf_b = !p.b_presplit;                       // pre-split weights are L2 hits anyway
+      // L2 prefetch iterator: the same (work item, k-block) sequence, pf_dist k-blocks ahead
+      const bool pf_b = !b_pre;                       // pre-split weights are L2 hits anyway
       int64_t pw = blockIdx.x, pk0 = 0, pkend = 0;
       auto pf_open = [&]() {
         if (pw >= num_work) return;
@@ -546,7 +560,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         while (pw < num_work && pk0 >= pkend) { pw += gridDim.x; pf_open(); }
         if (pw >= num_work) return;
         const int m0 = (int)((pw / p.tiles_n) % p.tiles_m) * BM, n0 = (int)(pw % p.tiles_n) * BN;
-        if (!p.a_mn_major) {
+        if (!a_mn) {
           if (p.K1 > 0 && pk0 >= p.K1) tma_prefetch_2d(&tmA2, (int)(pk0 - p.K1), m0);
           else tma_prefetch_2d(&tmA, (int)pk0, m0);
         } else {
@@ -554,7 +568,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           for (int b = 0; b < 4; ++b) tma_prefetch_2d(&tmA, m0 + 32 * b, (int)pk0);
         }
         if (pf_b) {
-          if (!p.b_mn_major) tma_prefetch_2d(&tmB, (int)pk0, n0);
+          if (!b_mn) tma_prefetch_2d(&tmB, (int)pk0, n0);
           else {
 #pragma unroll
             for (int b = 0; b < 4; ++b) tma_prefetch_2d(&tmB, n0 + 32 * b, (int)pk0);
@@ -562,9 +576,9 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         }
         pk0 += BK;
       };
-      if (p.prefetch > 0) {
+      if (pf_dist > 0) {
         pf_open();
-        for (int i = 0; i < p.prefetch; ++i) pf_step();
+        for (int i = 0; i < pf_dist; ++i) pf_step();
       }
       for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int nt = (int)(w % p.tiles_n);
@@ -574,12 +588,12 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         const int64_t kbeg = (int64_t)ks * p.k_per_split;
         const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
         for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-          if (p.prefetch > 0) pf_step();
-          mbar_wait_t(p.ticks, p.early_release ? &sfree_bar[stage] : &empty_bar[stage], phase ^ 1);
+          if (pf_dist > 0) pf_step();
+          mbar_wait_t(p.ticks, early_rel ? &sfree_bar[stage] : &empty_bar[stage], phase ^ 1);
           TRACE(0, tr_kb); ++tr_kb;
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&raw_bar[stage], (p.b_resident ? 1 : p.b_presplit ? 3 : 2) * TILE_BYTES);
-          if (!p.a_mn_major) {
+          mbar_arrive_expect_tx(&raw_bar[stage], (p.b_resident ? 1 : b_pre ? 3 : 2) * TILE_BYTES);
+          if (!a_mn) {
             if (p.K1 > 0 && k0 >= p.K1) tma_load_2d(st, &tmA2, (int)(k0 - p.K1), m0, &raw_bar[stage]);
             else tma_load_2d(st, &tmA, (int)k0, m0, &raw_bar[stage]);
           } else {
@@ -588,13 +602,13 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           }
           if (p.b_resident) {
             // B is in place
-          } else if (!p.b_mn_major) {
+          } else if (!b_mn) {
             tma_load_2d(st + TILE_BYTES, &tmB, (int)k0, n0, &raw_bar[stage]);
-            if (p.b_presplit) tma_load_2d(st + 2 * TILE_BYTES, &tmB2, (int)k0, n0, &raw_bar[stage]);
+            if (b_pre) tma_load_2d(st + 2 * TILE_BYTES, &tmB2, (int)k0, n0, &raw_bar[stage]);
           } else {
 #pragma unroll
             for (int b = 0; b < 4; ++b) tma_load_2d(st + TILE_BYTES + b * 4096, &tmB, n0 + 32 * b, (int)k0, &raw_bar[stage]);
-            if (p.b_presplit) {
+            if (b_pre) {
 #pragma unroll
               for (int b = 0; b < 4; ++b) tma_load_2d(st + 2 * TILE_BYTES + b * 4096, &tmB2, n0 + 32 * b, (int)k0, &raw_bar[stage]);
             }
@@ -623,7 +637,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           const int quarter = warp & 3, half = (warp - SPLIT_WARP0) >> 2;
           const int row = quarter * 32 + lane;
           uint32_t hi[16], lo[16];
-          if (!p.a_mn_major) {
+          if (!a_mn) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int c = half * 4 + i;                                   // 16-byte chunk of the 128-byte row
@@ -646,7 +660,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
               csum += x;
             }
           }
-          if (p.early_release) {
+          if (early_rel) {
             // the raw tile is in registers: hand the smem slot back to the TMA producer now (the arrive is a release: the
             // shared-memory reads above are ordered before it), then wait for the MMAs that read this TMEM slot four
             // k-blocks ago -- the smem ring now only holds bytes in flight, the TMEM ring the operands waiting for the MMA
@@ -660,7 +674,7 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           tmem_st16(taddr, hi);
           tmem_st16(taddr + BK, lo);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          if (!p.b_presplit) {
+          if (!b_pre) {
 #pragma unroll 4
             for (int i = 0; i < 1024 / SPLIT_THREADS; ++i) {
               const uint32_t bh = st_u32 + TILE_BYTES + (tt + SPLIT_THREADS * i) * 16;
@@ -681,11 +695,11 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         ++tr_kb;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (p.colsum_part != nullptr) {                        // bias gradient for free: A has just been read anyway
+      if (colsum_part != nullptr) {                        // bias gradient for free: A has just been read anyway
         const int nt = (int)(w % p.tiles_n);
         const int mt = (int)((w / p.tiles_n) % p.tiles_m);
         const int64_t m = (int64_t)mt * BM + (warp & 3) * 32 + lane;
-        if (nt == 0 && m < p.M) p.colsum_part[((int64_t)ks * 2 + ((warp - SPLIT_WARP0) >> 2)) * p.M + m] = csum;
+        if (nt == 0 && m < p.M) colsum_part[((int64_t)ks * 2 + ((warp - SPLIT_WARP0) >> 2)) * p.M + m] = csum;
       }
     }
   } else if (warp == MMA_WARP) {
@@ -696,8 +710,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
     uint32_t phase = 0, acc_phase = 0;
     // per k-step (8 tf32 = 32 bytes) descriptor advance: +32 B inside the swizzle row (K-major),
     // +1024 B = two 4-row k-atoms further (MN-major)
-    const uint32_t b_step = p.b_mn_major ? 1024u : 32u;
-    const uint64_t b_desc0 = make_desc(0, p.b_mn_major ? 4096u : 16u, p.b_mn_major ? 512u : 1024u, p.b_mn_major ? 1u : 2u);
+    const uint32_t b_step = b_mn ? 1024u : 32u;
+    const uint64_t b_desc0 = make_desc(0, b_mn ? 4096u : 16u, b_mn ? 512u : 1024u, b_mn ? 1u : 2u);
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t idesc = p.idesc;
     const int passes = p.passes;
@@ -771,18 +785,18 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      float* out = p.partial ? p.partial + (int64_t)(p.cta_acc ? (int)blockIdx.x : ks) * p.M * p.N : p.C;
-      const int64_t ldo = p.partial ? p.N : p.ldc;
+      float* out = partial ? partial + (int64_t)(cta_acc ? (int)blockIdx.x : ks) * p.M * p.N : p.C;
+      const int64_t ldo = partial ? p.N : p.ldc;
       const bool interior = p.c_vec && ((int64_t)(mt + 1) * BM <= p.M) && (n0 + BN <= p.N);
       // C += A.B (the GRU scan's per-step GEMMs), or this CTA's partial tile += its next split
-      const bool rmw = p.partial == nullptr ? (p.accumulate != 0) : (p.cta_acc != 0);
-      const bool bias_vec = p.partial == nullptr && p.bias != nullptr;       // host guarantees 16-byte alignment when c_vec
+      const bool rmw = partial == nullptr ? (accum_c != 0) : (cta_acc != 0);
+      const bool bias_vec = partial == nullptr && p.bias != nullptr;       // host guarantees 16-byte alignment when c_vec
       // The TMEM load of chunk cc+1 is issued as soon as the registers of chunk cc have gone to shared memory, so its latency
       // runs under the shared-memory read-back and the global stores of chunk cc (the epilogue warps are the slowest stage of
       // the pipeline for the [T*N, 128] projections: tools/trace_gemm.py).
       uint32_t r[32];
       const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-      const bool pipe = p.epi_pipe != 0;
+      const bool pipe = epi_pipe_on;
       if (has_k && pipe) tmem_ld32(taddr0, r);
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
@@ -848,8 +862,8 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
           }
           if (threadIdx.x == 0 && cc == 1) TRACE(11, tr_tile);
         } else {
-          const bool direct = p.partial == nullptr;
-          const bool acc_here = direct ? (p.accumulate != 0) : (p.cta_acc != 0);
+          const bool direct = partial == nullptr;
+          const bool acc_here = direct ? (accum_c != 0) : (cta_acc != 0);
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (direct && p.bias) {
             if (c0 < p.N) b4.x = p.bias[c0];
@@ -1060,7 +1074,7 @@ bool tagan_gemm_tma_supported(int64_t M, int64_t N, int64_t K, const float* A, i
   return get_encode() != nullptr;
 }
 
-static int g_st256 = 1;
+static int g_st256 = 1, g_simple = 1;
 static int g_b_resident = 1, g_prefetch = 0, g_epi_pipe = 0, g_early_release = 0, g_wait_ticks = 0x989680;
 void tagan_gemm_tma_set_tuning(int key, int value) {
   if (key == 0) g_b_resident = value;
@@ -1069,6 +1083,7 @@ void tagan_gemm_tma_set_tuning(int key, int value) {
   else if (key == 3) g_early_release = value;
   else if (key == 4) g_wait_ticks = value;
   else if (key == 5) g_st256 = value;
+  else if (key == 6) g_simple = value;
 }
 static long long* g_trace = nullptr;
 void tagan_gemm_tma_set_trace(void* buf) { g_trace = static_cast<long long*>(buf); }
@@ -1099,9 +1114,11 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
   if (dev < 0 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      e = cudaFuncSetAttribute(gemm_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0) attr_set[dev] = true;
   }
@@ -1199,8 +1216,11 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
     p.early_release = g_early_release;
     grid = 148 / pl.tiles_n * pl.tiles_n;
   }
-  if (p.fused) gemm_tma_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
-  else gemm_tma_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  const bool simple = g_simple && !p.fused && p.b_presplit && !p.a_mn_major && !p.b_mn_major && p.partial == nullptr && !accumulate &&
+                      p.colsum_part == nullptr && p.prefetch == 0 && !p.early_release && !p.epi_pipe && p.trace == nullptr;
+  if (p.fused) gemm_tma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  else if (simple) gemm_tma_kernel<false, true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  else gemm_tma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
   if (p.partial)
     tma_splitk_reduce<<<ceil_div_i64(M * N, 32), 256, 0, st>>>(p.partial, pl.parts, M, N, bias, C, ldc, accumulate);
   if (p.colsum_part)
