@@ -469,7 +469,9 @@ __device__ __forceinline__ void epilogue_fused(const Params& p, int warp, int la
 // SIMPLE = the shape of almost every projection of a step (pre-split K-major weights, no split-K, plain store, no profiling
 // knobs): the instantiation drops the MN-major / in-kernel-split / split-K / trace / prefetch code, which leaves a kernel a
 // quarter of the general one's size.
-template <bool FUSED, bool SIMPLE>
+// KIND 2 = the dW products (TN: both operands MN-major activations split in-kernel, split-K into CTA-private partial tiles):
+// the same specialisation for the other frequent shape.  KIND 0 = everything else.
+template <bool FUSED, int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmA2) {
@@ -486,17 +488,18 @@ gemm_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmA, const _
   const uint32_t epi_u32 = smem_u32(smem + (size_t)STAGES * STAGE_BYTES);      // 1024-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool a_mn = SIMPLE ? false : p.a_mn_major != 0;
-  const bool b_mn = SIMPLE ? false : p.b_mn_major != 0;
-  const bool b_pre = SIMPLE ? true : p.b_presplit != 0;
+  constexpr bool SIMPLE = KIND == 1, TNK = KIND == 2;
+  const bool a_mn = SIMPLE ? false : (TNK ? true : p.a_mn_major != 0);
+  const bool b_mn = SIMPLE ? false : (TNK ? true : p.b_mn_major != 0);
+  const bool b_pre = SIMPLE ? true : (TNK ? false : p.b_presplit != 0);
   float* const colsum_part = SIMPLE ? nullptr : p.colsum_part;
   float* const partial = SIMPLE ? nullptr : p.partial;
-  const int cta_acc = SIMPLE ? 0 : p.cta_acc;
-  const int accum_c = SIMPLE ? 0 : p.accumulate;
-  const int pf_dist = SIMPLE ? 0 : p.prefetch;
-  const bool early_rel = SIMPLE ? false : p.early_release != 0;
-  const bool epi_pipe_on = SIMPLE ? false : p.epi_pipe != 0;
-  long long* const trace_buf = SIMPLE ? nullptr : p.trace;
+  const int cta_acc = SIMPLE ? 0 : (TNK ? 1 : p.cta_acc);
+  const int accum_c = (SIMPLE || TNK) ? 0 : p.accumulate;
+  const int pf_dist = (SIMPLE || TNK) ? 0 : p.prefetch;
+  const bool early_rel = (SIMPLE || TNK) ? false : p.early_release != 0;
+  const bool epi_pipe_on = (SIMPLE || TNK) ? false : p.epi_pipe != 0;
+  long long* const trace_buf = (SIMPLE || TNK) ? nullptr : p.trace;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&raw_bar[s], 1); mbar_init(&full_bar[s], SPLIT_WARPS); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
@@ -1074,7 +1077,7 @@ bool tagan_gemm_tma_supported(int64_t M, int64_t N, int64_t K, const float* A, i
   return get_encode() != nullptr;
 }
 
-static int g_st256 = 1, g_simple = 1;
+static int g_st256 = 1, g_simple = 3;      // bit 0: KIND 1 (pre-split K-major weights), bit 1: KIND 2 (dW products)
 static int g_b_resident = 1, g_prefetch = 0, g_epi_pipe = 0, g_early_release = 0, g_wait_ticks = 0x989680;
 void tagan_gemm_tma_set_tuning(int key, int value) {
   if (key == 0) g_b_resident = value;
@@ -1114,11 +1117,13 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
   if (dev < 0 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      e = cudaFuncSetAttribute(gemm_tma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      e = cudaFuncSetAttribute(gemm_tma_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tma_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0) attr_set[dev] = true;
   }
@@ -1216,11 +1221,15 @@ int tagan_gemm_tma(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, 
     p.early_release = g_early_release;
     grid = 148 / pl.tiles_n * pl.tiles_n;
   }
-  const bool simple = g_simple && !p.fused && p.b_presplit && !p.a_mn_major && !p.b_mn_major && p.partial == nullptr && !accumulate &&
+  const bool simple = (g_simple & 1) && !p.fused && p.b_presplit && !p.a_mn_major && !p.b_mn_major && p.partial == nullptr && !accumulate &&
                       p.colsum_part == nullptr && p.prefetch == 0 && !p.early_release && !p.epi_pipe && p.trace == nullptr;
-  if (p.fused) gemm_tma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
-  else if (simple) gemm_tma_kernel<false, true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
-  else gemm_tma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  const bool knobs_off = p.prefetch == 0 && !p.early_release && !p.epi_pipe && p.trace == nullptr;
+  const bool tnk = (g_simple & 2) && !p.fused && p.a_mn_major && p.b_mn_major && !p.b_presplit && p.partial != nullptr && p.cta_acc &&
+                   knobs_off;
+  if (p.fused) gemm_tma_kernel<true, 0><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  else if (simple) gemm_tma_kernel<false, 1><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  else if (tnk) gemm_tma_kernel<false, 2><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
+  else gemm_tma_kernel<false, 0><<<grid, THREADS, SMEM_BYTES, st>>>(p, tmA, tmB, tmB2, tmA2);
   if (p.partial)
     tma_splitk_reduce<<<ceil_div_i64(M * N, 32), 256, 0, st>>>(p.partial, pl.parts, M, N, bias, C, ldc, accumulate);
   if (p.colsum_part)

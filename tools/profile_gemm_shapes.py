@@ -54,14 +54,14 @@ def main():
         lda, ldb = a.shape[1], b.shape[1]
         rec = {"case": "%s_%dx%dx%d" % (name, m, n, k)}
         nbytes = 4 * (a.numel() + c.numel() + b.numel())
-        # (256-bit epilogue stores, lean instantiation for pre-split K-major weights)
-        modes = [(1, 1), (1, 0), (1, 1), (1, 0)] if op != 2 else [(1, 1)]
+        # (256-bit epilogue stores, lean instantiations: bit 0 pre-split K-major weights, bit 1 dW products)
+        modes = [(1, 3), (1, 0), (1, 3), (1, 0)]
         for rep_i, mode in enumerate(modes):
             for key, val in zip((5, 6), mode):
                 lib.tagan_gemm_set_tuning(key, val)
             c.fill_(float("nan"))
             ms = timeit(lambda: ops.gemm(op, m, n, k, a, lda, b, ldb, bias, c, n))
-            key = "st256_%d_simple%d_run%d" % (mode + (rep_i // 2,)) 
+            key = "st256_%d_lean%d_run%d" % (mode + (rep_i // 2,)) 
             rec[key + "_ms"] = round(ms, 4)
             # float64 check on a sample of rows
             idx = torch.randint(0, m, (256,), device=dev)
@@ -76,7 +76,7 @@ def main():
             err = float((c[idx].double() - ref).abs().max() / ref.abs().max())
             rec[key + "_relerr"] = err
             assert err < 2e-5, (rec, err)
-        for key, val in ((0, 1), (2, 0), (3, 0), (4, 0x989680), (5, 1), (6, 1)):
+        for key, val in ((0, 1), (2, 0), (3, 0), (4, 0x989680), (5, 1), (6, 3)):
             lib.tagan_gemm_set_tuning(key, val)
         print(json.dumps(rec), flush=True)
         out.write(json.dumps(rec) + "\n")
