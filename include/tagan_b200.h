@@ -268,7 +268,8 @@ size_t tagan_gemm_fused_workspace_bytes(int32_t op, int64_t m, int64_t n, int64_
  *   key 3  resident mode: activation smem slots are released by the split warps instead of the MMA commit (default 0)
  *   key 4  suspend-time hint (ns) of the mbarrier waits, 0 = plain polling (default 10 000 000, as CUTLASS)
  *   key 5  256-bit global stores (STG.256) in the plain epilogue of interior tiles when C is 32-byte aligned (default 1)
- *   key 6  lean kernel instantiation for pre-split K-major weights without split-K / accumulate / knobs (default 1)
+ *   key 6  lean kernel instantiations (default 3): bit 0 pre-split K-major weights without split-K / accumulate / knobs,
+ *          bit 1 the dW products (TN, in-kernel split of both operands, CTA-private split-K partial tiles)
  * Keys 1-3 made no difference or a small loss in same-process A/B runs (profiles/r02_SUMMARY.md); they stay for re-measurement. */
 void tagan_gemm_set_tuning(int32_t key, int32_t value);
 /* Debug aid (tools/trace_gemm.py): a device buffer of 16 x 512 int64 that CTA 0 of every following tcgen05 GEMM launch
